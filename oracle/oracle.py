@@ -1,0 +1,711 @@
+"""CPU oracle for the gnark-crypto MultiExp (MSM) hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-Python (big-int) restatement of the reference algorithm for
+`ecc/<curve>.G1Jac.MultiExp` / `G2Jac.MultiExp`.  It is imported ONLY by `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline leg, as the checker.  The
+product path (gnark-crypto_b200/) never imports it.
+
+Parity pinning: the reference is Go and cannot be built here (no Go toolchain).  The
+oracle is pinned against everything the reference's own tests hold for this path:
+  * the generated field constants (qInvNeg, rSquare, One) -- see FIELDS[..]['pin'],
+    cited per field below;
+  * the curve generators (ecc/bn254/bn254.go:111-119, ecc/bls12-381/bls12-381.go:107-116);
+  * the hash-to-curve vectors with explicit affine points, identity P = Q0 + Q1 on
+    bn254 (ecc/bn254/hash_vectors_test.go:29-83, G2 :84+) -> tests/golden/;
+  * the relational MSM properties of ecc/bn254/multiexp_test.go:63-299 restated in
+    tests/test_oracle.py.
+There is no stored golden MSM output in the reference.
+
+All `file:line` citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Fields.  Everything else is derived, then pinned against the
+# generated constants quoted from the reference.
+# --------------------------------------------------------------------------------------
+
+
+class Field:
+    """Prime field with gnark-crypto's Montgomery representation.
+
+    ecc/bn254/fp/element.go:24-36 : an Element is [Limbs]uint64, little-endian, value*R mod q.
+    """
+
+    def __init__(self, name, q, limbs, pin):
+        self.name = name
+        self.q = q
+        self.limbs = limbs
+        self.bits = q.bit_length()
+        self.R = 1 << (64 * limbs)
+        self.Rmod = self.R % q  # "One" (SetOne, fp/element.go:194-200)
+        self.R2 = (self.R * self.R) % q  # rSquare (fp/element.go:773)
+        self.Rinv = pow(self.R, -1, q)
+        # field/generator/config/field_config.go:140-183 : qInvNeg = -q^{-1} mod 2^64
+        self.qinvneg = (-pow(q, -1, 1 << 64)) % (1 << 64)
+        self.pin = pin
+
+    # ---- Montgomery edges (fp/element.go:593-642 fromMont, :782-784 toMont) ----
+    def to_mont(self, a: int) -> int:
+        return (a * self.R) % self.q
+
+    def from_mont(self, m: int) -> int:
+        return (m * self.Rinv) % self.q
+
+    def to_limbs(self, v: int):
+        return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(self.limbs)]
+
+    @staticmethod
+    def from_limbs(l) -> int:
+        v = 0
+        for i, w in enumerate(l):
+            v |= int(w) << (64 * i)
+        return v
+
+    # ---- textbook CIOS on 64-bit limbs: _mulGeneric, fp/element.go:470-591 ----
+    def mont_mul_cios(self, x: int, y: int) -> int:
+        """x, y Montgomery-form integers < q -> x*y*R^-1 mod q, computed limb by limb
+        exactly as the reference's generic CIOS (used to pin the device CIOS)."""
+        N = self.limbs
+        M = 0xFFFFFFFFFFFFFFFF
+        xl, yl, ql = self.to_limbs(x), self.to_limbs(y), self.to_limbs(self.q)
+        t = [0] * (N + 2)
+        for i in range(N):
+            c = 0
+            for j in range(N):
+                s = t[j] + xl[j] * yl[i] + c
+                t[j] = s & M
+                c = s >> 64
+            s = t[N] + c
+            t[N] = s & M
+            t[N + 1] = s >> 64
+            m = (t[0] * self.qinvneg) & M
+            s = t[0] + m * ql[0]
+            c = s >> 64
+            for j in range(1, N):
+                s = t[j] + m * ql[j] + c
+                t[j - 1] = s & M
+                c = s >> 64
+            s = t[N] + c
+            t[N - 1] = s & M
+            t[N] = t[N + 1] + (s >> 64)
+        z = self.from_limbs(t[:N]) + (t[N] << (64 * N))
+        if z >= self.q:  # fp/element.go:583-590
+            z -= self.q
+        return z
+
+
+FIELDS = {
+    # ecc/bn254/fp/element.go:31,39-50,71,195-198,773
+    "bn254_fp": Field(
+        "bn254_fp",
+        0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47,
+        4,
+        dict(
+            qinvneg=9786893198990664585,
+            rsquare=[17522657719365597833, 13107472804851548667, 5164255478447964150, 493319470278259999],
+        ),
+    ),
+    # ecc/bn254/fr/element.go:31,39-49,71,773-778
+    "bn254_fr": Field(
+        "bn254_fr",
+        0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
+        4,
+        dict(
+            qinvneg=14042775128853446655,
+            rsquare=[1997599621687373223, 6052339484930628067, 10108755138030829701, 150537098327114917],
+        ),
+    ),
+    # ecc/bls12-381/fp/element.go:31,38-51,75,928-935
+    "bls12381_fp": Field(
+        "bls12381_fp",
+        0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB,
+        6,
+        dict(
+            qinvneg=9940570264628428797,
+            rsquare=[
+                17644856173732828998,
+                754043588434789617,
+                10224657059481499349,
+                7488229067341005760,
+                11130996698012816685,
+                1267921511277847466,
+            ],
+        ),
+    ),
+    # ecc/bls12-381/fr/element.go:31,39-49,71,773-778
+    "bls12381_fr": Field(
+        "bls12381_fr",
+        0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+        4,
+        dict(
+            qinvneg=18446744069414584319,
+            rsquare=[14526898881837571181, 3129137299524312099, 419701826671360399, 524908885293268753],
+        ),
+    ),
+}
+
+
+# --------------------------------------------------------------------------------------
+# Coordinate-field adapters: Fp (ints mod q) and Fp2 = Fp[u]/(u^2+1) (tuples).
+# Values here are PLAIN integers (not Montgomery); SURVEY.md A.1 -- Montgomery form is
+# closed under the ops, so we encode only at the edges and the encoded result is unique.
+# --------------------------------------------------------------------------------------
+
+
+class FpOps:
+    ext = 1
+
+    def __init__(self, field: Field):
+        self.f = field
+        self.q = field.q
+        self.zero = 0
+        self.one = 1
+
+    def add(self, a, b):
+        return (a + b) % self.q
+
+    def sub(self, a, b):
+        return (a - b) % self.q
+
+    def neg(self, a):
+        return (-a) % self.q
+
+    def dbl(self, a):
+        return (2 * a) % self.q
+
+    def mul(self, a, b):
+        return (a * b) % self.q
+
+    def sqr(self, a):
+        return (a * a) % self.q
+
+    def inv(self, a):
+        # fp.Inverse(0) = 0 (fp/element.go:1170-1172)
+        return 0 if a == 0 else pow(a, -1, self.q)
+
+    def is_zero(self, a):
+        return a == 0
+
+    def from_int(self, v):
+        return v % self.q
+
+    # memory edges: L u64 limbs of the Montgomery representation
+    def encode(self, a):
+        return self.f.to_limbs(self.f.to_mont(a))
+
+    def decode(self, limbs):
+        return self.f.from_mont(Field.from_limbs(limbs))
+
+    @property
+    def words(self):
+        return self.f.limbs
+
+
+class Fp2Ops:
+    """E2 = A0 + A1*u, u^2 = -1 (ecc/bn254/internal/fptower/e2.go:14-16, e2_bn254.go:28-73;
+    same formulas ecc/bls12-381/internal/fptower/e2_bls381.go:16-74)."""
+
+    ext = 2
+
+    def __init__(self, field: Field):
+        self.f = field
+        self.q = field.q
+        self.zero = (0, 0)
+        self.one = (1, 0)
+
+    def add(self, a, b):
+        return ((a[0] + b[0]) % self.q, (a[1] + b[1]) % self.q)
+
+    def sub(self, a, b):
+        return ((a[0] - b[0]) % self.q, (a[1] - b[1]) % self.q)
+
+    def neg(self, a):
+        return ((-a[0]) % self.q, (-a[1]) % self.q)
+
+    def dbl(self, a):
+        return ((2 * a[0]) % self.q, (2 * a[1]) % self.q)
+
+    def mul(self, a, b):
+        # e2_bn254.go:28-38 (Karatsuba)
+        q = self.q
+        ac = a[0] * b[0] % q
+        bd = a[1] * b[1] % q
+        t = (a[0] + a[1]) * (b[0] + b[1]) % q
+        return ((ac - bd) % q, (t - ac - bd) % q)
+
+    def sqr(self, a):
+        # e2_bn254.go:41-51
+        q = self.q
+        return ((a[0] + a[1]) * (a[0] - a[1]) % q, (2 * a[0] * a[1]) % q)
+
+    def inv(self, a):
+        # e2_bn254.go:61-73
+        q = self.q
+        n = (a[0] * a[0] + a[1] * a[1]) % q
+        ni = 0 if n == 0 else pow(n, -1, q)
+        return (a[0] * ni % q, (-a[1] * ni) % q)
+
+    def is_zero(self, a):
+        return a[0] == 0 and a[1] == 0
+
+    def from_int(self, v):
+        return (v % self.q, 0)
+
+    def encode(self, a):
+        return self.f.to_limbs(self.f.to_mont(a[0])) + self.f.to_limbs(self.f.to_mont(a[1]))
+
+    def decode(self, limbs):
+        L = self.f.limbs
+        return (self.f.from_mont(Field.from_limbs(limbs[:L])), self.f.from_mont(Field.from_limbs(limbs[L:])))
+
+    @property
+    def words(self):
+        return 2 * self.f.limbs
+
+
+# --------------------------------------------------------------------------------------
+# Groups
+# --------------------------------------------------------------------------------------
+
+INF_AFF = None  # python-side marker; in memory the affine infinity is (0,0) (g1.go:41-47,178-180)
+
+
+class Group:
+    """Short-Weierstrass group y^2 = x^3 + b (a = 0; g1.go:804) over FpOps / Fp2Ops.
+
+    Affine points are (x, y) tuples of coordinate-field values, or (zero, zero) for infinity
+    exactly as in Go memory.  xyzz points are [X, Y, ZZ, ZZZ] lists; infinity iff ZZ == 0
+    (g1.go:688-699).
+    """
+
+    def __init__(self, name, K, fr: Field, b, gen):
+        self.name = name
+        self.K = K
+        self.fr = fr
+        self.b = b
+        self.gen = gen
+
+    # ---- predicates ----
+    def aff_is_inf(self, a):
+        return self.K.is_zero(a[0]) and self.K.is_zero(a[1])
+
+    def aff_inf(self):
+        return (self.K.zero, self.K.zero)
+
+    def is_on_curve(self, a):
+        K = self.K
+        if self.aff_is_inf(a):
+            return True
+        return K.sqr(a[1]) == K.add(K.mul(K.sqr(a[0]), a[0]), self.b)
+
+    def aff_neg(self, a):
+        return (a[0], self.K.neg(a[1]))
+
+    # ---- xyzz formulas, SURVEY.md A.4 / A.5 ----
+    def xyzz_inf(self):
+        K = self.K
+        return [K.one, K.one, K.zero, K.zero]  # SetInfinity g1.go:688-694
+
+    def _double_mixed(self, a, negate):
+        # doubleMixed g1.go:962-985 ; doubleNegMixed :933-957
+        K = self.K
+        y = K.neg(a[1]) if negate else a[1]
+        U = K.dbl(y)
+        V = K.sqr(U)
+        W = K.mul(U, V)
+        S = K.mul(a[0], V)
+        XX = K.sqr(a[0])
+        M = K.add(K.dbl(XX), XX)
+        S2 = K.dbl(S)
+        L = K.mul(W, y)
+        X3 = K.sub(K.sqr(M), S2)
+        Y3 = K.sub(K.mul(K.sub(S, X3), M), L)
+        return [X3, Y3, V, W]
+
+    def add_mixed(self, p, a, negate=False):
+        """p (xyzz, mutated copy returned) += a (affine), or -= a if negate.
+        addMixed g1.go:822-873, subMixed :878-930."""
+        K = self.K
+        if self.aff_is_inf(a):
+            return p
+        ay = K.neg(a[1]) if negate else a[1]
+        if K.is_zero(p[2]):
+            return [a[0], ay, K.one, K.one]
+        P = K.sub(K.mul(a[0], p[2]), p[0])
+        R = K.sub(K.mul(ay, p[3]), p[1])
+        if K.is_zero(P):
+            if K.is_zero(R):
+                return self._double_mixed(a, negate)
+            return [p[0], p[1], K.zero, K.zero]
+        PP = K.sqr(P)
+        PPP = K.mul(P, PP)
+        Q = K.mul(p[0], PP)
+        RR = K.sqr(R)
+        X3 = K.sub(K.sub(RR, PPP), K.dbl(Q))
+        Y3 = K.sub(K.mul(K.sub(Q, X3), R), K.mul(p[1], PPP))
+        return [X3, Y3, K.mul(p[2], PP), K.mul(p[3], PPP)]
+
+    def xyzz_double(self, q):
+        # double g1.go:795-817 (valid for infinity)
+        K = self.K
+        U = K.dbl(q[1])
+        V = K.sqr(U)
+        W = K.mul(U, V)
+        S = K.mul(q[0], V)
+        XX = K.sqr(q[0])
+        M = K.add(K.dbl(XX), XX)
+        U2 = K.mul(W, q[1])
+        X3 = K.sub(K.sub(K.sqr(M), S), S)
+        Y3 = K.sub(K.mul(K.sub(S, X3), M), U2)
+        return [X3, Y3, K.mul(V, q[2]), K.mul(W, q[3])]
+
+    def xyzz_add(self, p, q):
+        # add g1.go:736-788
+        K = self.K
+        if K.is_zero(q[2]):
+            return p
+        if K.is_zero(p[2]):
+            return list(q)
+        U2 = K.mul(q[0], p[2])
+        U1 = K.mul(p[0], q[2])
+        S2 = K.mul(q[1], p[3])
+        S1 = K.mul(p[1], q[3])
+        P = K.sub(U2, U1)
+        R = K.sub(S2, S1)
+        if K.is_zero(P):
+            if K.is_zero(R):
+                return self.xyzz_double(q)
+            return [p[0], p[1], K.zero, K.zero]
+        PP = K.sqr(P)
+        PPP = K.mul(P, PP)
+        Q = K.mul(U1, PP)
+        V = K.mul(S1, PPP)
+        X3 = K.sub(K.sub(K.sub(K.sqr(R), PPP), Q), Q)
+        Y3 = K.sub(K.mul(K.sub(Q, X3), R), V)
+        return [X3, Y3, K.mul(K.mul(p[2], q[2]), PP), K.mul(K.mul(p[3], q[3]), PPP)]
+
+    # ---- conversions, SURVEY.md A.7 ----
+    def xyzz_to_jac(self, p):
+        """unsafeFromJacExtended g1.go:726-731 : (ZZ^2 X, ZZZ^2 Y, ZZZ); infinity -> (0,0,0)."""
+        K = self.K
+        if K.is_zero(p[2]):
+            # ZZ = ZZZ = 0 -> the products are all zero
+            return (K.zero, K.zero, K.zero)
+        return (K.mul(K.sqr(p[2]), p[0]), K.mul(K.sqr(p[3]), p[1]), p[3])
+
+    def jac_to_affine(self, j):
+        """FromJacobian g1.go:150-166"""
+        K = self.K
+        if K.is_zero(j[2]):
+            return self.aff_inf()
+        a = K.inv(j[2])
+        b = K.sqr(a)
+        return (K.mul(j[0], b), K.mul(K.mul(j[1], b), a))
+
+    def xyzz_to_affine(self, p):
+        return self.jac_to_affine(self.xyzz_to_jac(p))
+
+    # ---- plain affine arithmetic, used only to build inputs / closed forms in tests ----
+    def aff_add(self, p, q):
+        K = self.K
+        if self.aff_is_inf(p):
+            return q
+        if self.aff_is_inf(q):
+            return p
+        if p[0] == q[0]:
+            if p[1] == q[1]:
+                lam = K.mul(K.mul(K.from_int(3), K.sqr(p[0])), K.inv(K.dbl(p[1])))
+            else:
+                return self.aff_inf()
+        else:
+            lam = K.mul(K.sub(q[1], p[1]), K.inv(K.sub(q[0], p[0])))
+        x3 = K.sub(K.sub(K.sqr(lam), p[0]), q[0])
+        y3 = K.sub(K.mul(lam, K.sub(p[0], x3)), p[1])
+        return (x3, y3)
+
+    def scalar_mul(self, p, k: int):
+        """double-and-add on xyzz; k any non-negative integer."""
+        acc = self.xyzz_inf()
+        if k < 0:
+            p, k = self.aff_neg(p), -k
+        for bit in bin(k)[2:] if k else "":
+            acc = self.xyzz_double(acc)
+            if bit == "1":
+                acc = self.add_mixed(acc, p)
+        return self.xyzz_to_affine(acc)
+
+    # ---- memory layout: n x {X, Y} u64 LE Montgomery; infinity = zeros ----
+    @property
+    def aff_words(self):
+        return 2 * self.K.words
+
+    def encode_affine(self, pts) -> np.ndarray:
+        out = np.zeros((len(pts), self.aff_words), dtype=np.uint64)
+        for i, a in enumerate(pts):
+            if self.aff_is_inf(a):
+                continue
+            out[i, :] = np.array(self.K.encode(a[0]) + self.K.encode(a[1]), dtype=np.uint64)
+        return out
+
+    def decode_affine(self, arr) -> list:
+        w = self.K.words
+        arr = np.asarray(arr, dtype=np.uint64).reshape(-1, 2 * w)
+        return [(self.K.decode([int(v) for v in r[:w]]), self.K.decode([int(v) for v in r[w:]])) for r in arr]
+
+    def encode_jac(self, j) -> np.ndarray:
+        return np.array(self.K.encode(j[0]) + self.K.encode(j[1]) + self.K.encode(j[2]), dtype=np.uint64)
+
+    def decode_jac(self, arr):
+        w = self.K.words
+        l = [int(v) for v in np.asarray(arr, dtype=np.uint64).reshape(-1)]
+        return (self.K.decode(l[:w]), self.K.decode(l[w : 2 * w]), self.K.decode(l[2 * w : 3 * w]))
+
+    def encode_scalars(self, ks) -> np.ndarray:
+        """integers in [0, r) -> n x 4 u64, Montgomery form (what Go passes)."""
+        out = np.zeros((len(ks), self.fr.limbs), dtype=np.uint64)
+        for i, k in enumerate(ks):
+            out[i, :] = np.array(self.fr.to_limbs(self.fr.to_mont(k % self.fr.q)), dtype=np.uint64)
+        return out
+
+    def decode_scalars(self, arr) -> list:
+        arr = np.asarray(arr, dtype=np.uint64).reshape(-1, self.fr.limbs)
+        return [self.fr.from_mont(Field.from_limbs([int(v) for v in r])) for r in arr]
+
+
+def _mk_groups():
+    bn_fp, bn_fr = FIELDS["bn254_fp"], FIELDS["bn254_fr"]
+    bl_fp, bl_fr = FIELDS["bls12381_fp"], FIELDS["bls12381_fr"]
+    g = {}
+    # ecc/bn254/bn254.go:12-13,105-119 : Y^2 = X^3 + 3, generator (1, 2)
+    K = FpOps(bn_fp)
+    g["bn254_g1"] = Group("bn254_g1", K, bn_fr, 3, (1, 2))
+    # twist b' = 3/(9+u)  (bn254.go:106-109); generator bn254.go:115-118
+    K2 = Fp2Ops(bn_fp)
+    bt = K2.mul(K2.inv((9, 1)), (3, 0))
+    g["bn254_g2"] = Group(
+        "bn254_g2",
+        K2,
+        bn_fr,
+        bt,
+        (
+            (
+                10857046999023057135944570762232829481370756359578518086990519993285655852781,
+                11559732032986387107991004021392285783925812861821192530917403151452391805634,
+            ),
+            (
+                8495653923123431417604973247489272438418190587263600148770280649306958101930,
+                4082367875863433681332203403145435568316851327593401208105741076214120093531,
+            ),
+        ),
+    )
+    # ecc/bls12-381/bls12-381.go:9-10,100-116 : Y^2 = X^3 + 4 ; twist b' = 4(1+u)
+    K = FpOps(bl_fp)
+    g["bls12381_g1"] = Group(
+        "bls12381_g1",
+        K,
+        bl_fr,
+        4,
+        (
+            3685416753713387016781088315183077757961620795782546409894578378688607592378376318836054947676345821548104185464507,
+            1339506544944476473020471379941921221584933875938349620426543736416511423956333506472724655353366534992391756441569,
+        ),
+    )
+    K2 = Fp2Ops(bl_fp)
+    g["bls12381_g2"] = Group(
+        "bls12381_g2",
+        K2,
+        bl_fr,
+        K2.mul((1, 1), (4, 0)),
+        (
+            (
+                352701069587466618187139116011060144890029952792775240219908644239793785735715026873347600343865175952761926303160,
+                3059144344244213709971259814753781636986470325476647558659373206291635324768958432433509563104347017837885763365758,
+            ),
+            (
+                1985150602287291935568054521177171638300868978215655730859378665066344726373823718423869104263333984641494340347905,
+                927553665492332455747201965776037880757740193453592970025027978793976877002675564980949289727957565575433344219582,
+            ),
+        ),
+    )
+    return g
+
+
+GROUPS = _mk_groups()
+
+
+# --------------------------------------------------------------------------------------
+# MSM
+# --------------------------------------------------------------------------------------
+
+
+def compute_nb_chunks(bits: int, c: int) -> int:
+    """computeNbChunks multiexp.go:681-683"""
+    return (bits + c - 1) // c
+
+
+def last_c(bits: int, c: int) -> int:
+    """lastC multiexp.go:690-693"""
+    nb_available = compute_nb_chunks(bits, c) * c - bits
+    return c + 1 - nb_available
+
+
+def best_c(bits: int, n: int, cs=range(4, 17)) -> int:
+    """bestC multiexp.go:75-93"""
+    best, bc = None, None
+    for c in cs:
+        cost = float((bits + 1) * (n + (1 << c))) / float(c)
+        if best is None or cost < best:
+            best, bc = cost, c
+    return bc
+
+
+def partition_scalars(fr: Field, scalars_mont, c: int) -> np.ndarray:
+    """partitionScalars multiexp.go:709-803.
+
+    scalars_mont: iterable of Montgomery-form integers (< r) as Go holds them.
+    Returns digits[chunk][i] as uint32 (the reference stores uint16 since its c <= 16;
+    the encoding is the same: 0 skip, 2d for d>0, 2(-d-1)+1 for d<0; last chunk 2d).
+    """
+    scalars_mont = list(scalars_mont)
+    n = len(scalars_mont)
+    W = compute_nb_chunks(fr.bits, c)
+    digits = np.zeros((W, n), dtype=np.uint32)
+    mask = (1 << c) - 1
+    mx = (1 << (c - 1)) - 1
+    limbs = fr.limbs
+    for i, s in enumerate(scalars_mont):
+        if s == 0:  # IsZero() on the Montgomery limbs, multiexp.go:743
+            continue
+        k = fr.from_mont(s)  # Bits(), fr/element.go:855-859
+        kl = fr.to_limbs(k)
+        carry = 0
+        for ch in range(W):
+            jc = ch * c
+            idx = jc // 64
+            shift = jc - idx * 64
+            # selector logic multiexp.go:729-737 (bits beyond the last limb read as absent)
+            d = carry + (((kl[idx] & ((mask << shift) & 0xFFFFFFFFFFFFFFFF)) >> shift) if idx < limbs else 0)
+            multi = (64 % c != 0) and shift > (64 - c) and idx < limbs - 1
+            if multi:
+                nb_hi = shift - (64 - c)
+                d += (kl[idx + 1] & ((1 << nb_hi) - 1)) << (c - nb_hi)
+            if ch < W - 1:
+                carry = 0
+                if d > mx:
+                    d -= 1 << c
+                    carry = 1
+                if d == 0:
+                    continue
+                digits[ch, i] = (d << 1) if d > 0 else (((-d - 1) << 1) + 1)
+            else:
+                digits[ch, i] = d << 1  # multiexp.go:788-800
+    return digits
+
+
+def process_chunk(G: Group, c_eff: int, points, digits_row):
+    """processChunkG1Jacobian multiexp_jacobian.go:8-61 -> window total (xyzz)."""
+    nb = 1 << (c_eff - 1)
+    buckets = [G.xyzz_inf() for _ in range(nb)]
+    for i, e in enumerate(digits_row):
+        e = int(e)
+        if e == 0:
+            continue
+        if e & 1 == 0:
+            buckets[(e >> 1) - 1] = G.add_mixed(buckets[(e >> 1) - 1], points[i])
+        else:
+            buckets[e >> 1] = G.add_mixed(buckets[e >> 1], points[i], negate=True)
+    run, tot = G.xyzz_inf(), G.xyzz_inf()
+    for k in range(nb - 1, -1, -1):
+        if not G.K.is_zero(buckets[k][2]):
+            run = G.xyzz_add(run, buckets[k])
+        tot = G.xyzz_add(tot, run)
+    return tot
+
+
+def reduce_chunks(G: Group, c: int, totals):
+    """msmReduceChunkG1Affine multiexp.go:302-315 -> Jacobian triple."""
+    acc = list(totals[-1])
+    for j in range(len(totals) - 2, -1, -1):
+        for _ in range(c):
+            acc = G.xyzz_double(acc)
+        acc = G.xyzz_add(acc, totals[j])
+    return G.xyzz_to_jac(acc)
+
+
+def inner_msm(G: Group, c: int, points, scalars_mont):
+    """_innerMsmG1 multiexp.go:148-209 (sequential restatement). Returns Jacobian triple."""
+    fr = G.fr
+    W = compute_nb_chunks(fr.bits, c)
+    digits = partition_scalars(fr, scalars_mont, c)
+    totals = []
+    for j in range(W):
+        ce = last_c(fr.bits, c) if j == W - 1 else c
+        totals.append(process_chunk(G, ce, points, digits[j]))
+    return reduce_chunks(G, c, totals)
+
+
+def multi_exp(G: Group, points, scalars_mont, c=None):
+    """(*G1Jac).MultiExp multiexp.go:32-146 without the (result-preserving) split. -> affine."""
+    if len(points) != len(scalars_mont):
+        raise ValueError("len(points) != len(scalars)")
+    if c is None:
+        c = best_c(G.fr.bits, len(points))
+    return G.jac_to_affine(inner_msm(G, c, points, scalars_mont))
+
+
+def msm_naive(G: Group, points, ks):
+    """sum k_i * P_i by independent double-and-add (independent of the bucket method)."""
+    acc = G.aff_inf()
+    for p, k in zip(points, ks):
+        acc = G.aff_add(acc, G.scalar_mul(p, k))
+    return acc
+
+
+# --------------------------------------------------------------------------------------
+# deterministic synthetic inputs
+# --------------------------------------------------------------------------------------
+
+M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def splitmix64(state: int):
+    state = (state + 0x9E3779B97F4A7C15) & M64
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return state, z ^ (z >> 31)
+
+
+def random_scalars_mont(fr: Field, n: int, seed: int):
+    """n uniform values < r, 4 x u64 with top bits masked to fr.bits and rejection-sampled
+    (analogue of SetRandom fr/element.go:302-343); the limbs are read AS the Montgomery
+    representation.  Scalar i depends only on (seed, i): state = seed + i*2^32 stream."""
+    out = []
+    topmask = (1 << (fr.bits - 64 * (fr.limbs - 1))) - 1
+    for i in range(n):
+        st = (seed ^ (i * 0xD1342543DE82EF95)) & M64
+        while True:
+            limbs = []
+            for _ in range(fr.limbs):
+                st, v = splitmix64(st)
+                limbs.append(v)
+            limbs[-1] &= topmask
+            v = Field.from_limbs(limbs)
+            if v < fr.q:
+                out.append(v)
+                break
+    return out
+
+
+def consecutive_multiples(G: Group, n: int, start_k: int = 1, base=None):
+    """[start_k]B, [start_k+1]B, ... as in TestCrossMultiExpG1 (multiexp_test.go:224-230)."""
+    base = base if base is not None else G.gen
+    p = G.scalar_mul(base, start_k)
+    out = []
+    for _ in range(n):
+        out.append(p)
+        p = G.aff_add(p, base)
+    return out

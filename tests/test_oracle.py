@@ -1,0 +1,238 @@
+"""Pins the CPU oracle (oracle/oracle.py) against what the reference's own tests hold for the
+MSM path: generated constants, generators, hash-to-curve known answers, and the relational MSM
+properties of ecc/bn254/multiexp_test.go (restated).  CPU only."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hash_vectors.json")))
+
+
+@pytest.mark.parametrize("name", list(O.FIELDS))
+def test_field_constants_match_generated(name):
+    f = O.FIELDS[name]
+    assert f.qinvneg == f.pin["qinvneg"]
+    assert f.to_limbs(f.R2) == f.pin["rsquare"]
+
+
+def test_one_limbs_bn254_fr():
+    # fr.IsOne constants, ecc/bn254/fr/element.go:227
+    f = O.FIELDS["bn254_fr"]
+    assert f.to_limbs(f.Rmod) == [12436184717236109307, 3962172157175319849, 7381016538464732718, 1011752739694698287]
+
+
+@pytest.mark.parametrize("name", list(O.FIELDS))
+def test_cios_matches_bigint(name):
+    f = O.FIELDS[name]
+    rng = random.Random(1)
+    specials = [0, 1, f.q - 1, f.Rmod, f.R2, (f.q - 1) // 2]
+    vals = specials + [rng.randrange(f.q) for _ in range(40)]
+    for a in vals:
+        for b in vals[:12]:
+            assert f.mont_mul_cios(a, b) == (a * b * f.Rinv) % f.q
+    # round trip
+    for a in vals:
+        assert f.from_mont(f.to_mont(a)) == a
+
+
+@pytest.mark.parametrize("name", list(O.GROUPS))
+def test_generators_on_curve_and_order(name):
+    G = O.GROUPS[name]
+    assert G.is_on_curve(G.gen)
+    assert G.aff_is_inf(G.scalar_mul(G.gen, G.fr.q))
+    assert G.scalar_mul(G.gen, G.fr.q + 5) == G.scalar_mul(G.gen, 5)
+
+
+def _pt(G, s):
+    if G.K.ext == 1:
+        return (int(s[0], 16), int(s[1], 16))
+    x = tuple(int(v, 16) for v in s[0].split(","))
+    y = tuple(int(v, 16) for v in s[1].split(","))
+    return (x, y)
+
+
+def test_bn254_hash_vectors_addition_known_answer():
+    # hash_to_curve: P = clear_cofactor(Q0 + Q1); bn254 G1 cofactor is 1 (g1.go:475-482)
+    G = O.GROUPS["bn254_g1"]
+    cases = GOLD["bn254"]["vectors"]["hashToG1Vector"]
+    assert len(cases) == 5
+    for c in cases:
+        P, Q0, Q1 = _pt(G, c["P"]), _pt(G, c["Q0"]), _pt(G, c["Q1"])
+        for p in (P, Q0, Q1):
+            assert G.is_on_curve(p)
+        assert G.aff_add(Q0, Q1) == P
+        # the same through the xyzz formulas the MSM uses
+        acc = G.add_mixed(G.xyzz_inf(), Q0)
+        acc = G.add_mixed(acc, Q1)
+        assert G.xyzz_to_affine(acc) == P
+        acc2 = G.xyzz_add(G.add_mixed(G.xyzz_inf(), Q0), G.add_mixed(G.xyzz_inf(), Q1))
+        assert G.xyzz_to_affine(acc2) == P
+        # subMixed: P - Q1 = Q0
+        assert G.xyzz_to_affine(G.add_mixed(G.add_mixed(G.xyzz_inf(), P), Q1, negate=True)) == Q0
+
+
+def test_bls12381_g1_hash_vectors_known_answer():
+    # RFC 9380 8.8.1: h_eff = 0xd201000000010001 ; ecc/bls12-381/hash_vectors_test.go
+    G = O.GROUPS["bls12381_g1"]
+    for c in GOLD["bls12381"]["vectors"]["hashToG1Vector"]:
+        P, Q0, Q1 = _pt(G, c["P"]), _pt(G, c["Q0"]), _pt(G, c["Q1"])
+        for p in (P, Q0, Q1):
+            assert G.is_on_curve(p)
+        assert G.scalar_mul(G.aff_add(Q0, Q1), 0xD201000000010001) == P
+
+
+@pytest.mark.parametrize("curve,g", [("bn254", "bn254_g2"), ("bls12381", "bls12381_g2")])
+def test_g2_vectors_on_twist(curve, g):
+    G = O.GROUPS[g]
+    vec = GOLD[curve]["vectors"]
+    n = 0
+    for c in vec["hashToG2Vector"] + vec["encodeToG2Vector"]:
+        for k in ("P", "Q0", "Q1", "Q"):
+            if k in c:
+                assert G.is_on_curve(_pt(G, c[k]))
+                n += 1
+    assert n >= 20
+
+
+def test_bls12381_g2_hash_vector_known_answer():
+    # RFC 9380 8.8.2 effective cofactor for G2
+    h_eff = 0xBC69F08F2EE75B3584C6A0EA91B352888E2A8E9145AD7689986FF031508FFE1329C2F178731DB956D82BF015D1212B02EC0EC69D7477C1AE954CBC06689F6A359894C0ADEBBF6B4E8020005AAA95551
+    G = O.GROUPS["bls12381_g2"]
+    c = GOLD["bls12381"]["vectors"]["hashToG2Vector"][0]
+    P, Q0, Q1 = _pt(G, c["P"]), _pt(G, c["Q0"]), _pt(G, c["Q1"])
+    assert G.scalar_mul(G.aff_add(Q0, Q1), h_eff) == P
+
+
+# ---------------------------------------------------------------------------------------
+# digits
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr"])
+@pytest.mark.parametrize("c", [2, 3, 5, 8, 11, 13, 14, 15, 16, 20, 23])
+def test_partition_scalars_reconstructs(frname, c):
+    fr = O.FIELDS[frname]
+    rng = random.Random(c)
+    ks = [0, 1, fr.q - 1, fr.q - 2, (1 << (fr.bits - 1)), (1 << c) - 1, 1 << (c - 1)] + [rng.randrange(fr.q) for _ in range(30)]
+    sm = [fr.to_mont(k) for k in ks]
+    d = O.partition_scalars(fr, sm, c)
+    W = O.compute_nb_chunks(fr.bits, c)
+    assert d.shape == (W, len(ks))
+    lc = O.last_c(fr.bits, c)
+    for i, k in enumerate(ks):
+        v = 0
+        for j in range(W):
+            e = int(d[j, i])
+            if e == 0:
+                continue
+            if j == W - 1:
+                assert e & 1 == 0
+                m = e >> 1
+                assert m - 1 < (1 << (lc - 1))
+            else:
+                m = (e >> 1) if e & 1 == 0 else -((e >> 1) + 1)
+                assert abs(m) <= (1 << (c - 1))
+                assert (abs(m) - 1) < (1 << (c - 1))
+            v += m << (c * j)
+        assert v == k
+
+
+def test_lastc_values():
+    # SURVEY.md A.2 examples
+    assert O.last_c(254, 16) == 15 and O.last_c(255, 16) == 16 and O.last_c(254, 11) == 2
+    assert O.compute_nb_chunks(254, 16) == 16 and O.compute_nb_chunks(254, 13) == 20
+    assert O.best_c(254, 1 << 16) == 13 and O.best_c(254, 1 << 20) == 16
+
+
+# ---------------------------------------------------------------------------------------
+# MSM relational properties (ecc/bn254/multiexp_test.go)
+# ---------------------------------------------------------------------------------------
+
+
+def _inputs(G, n, seed, n_inf=0):
+    rng = random.Random(seed)
+    mixer = rng.randrange(1, G.fr.q)
+    pts = O.consecutive_multiples(G, n)
+    ks = [((i + 1) * mixer) % G.fr.q for i in range(n)]
+    for _ in range(n_inf):
+        pts[rng.randrange(n)] = G.aff_inf()
+    return pts, ks
+
+
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bn254_g2"])
+def test_msm_all_c_agree(g):
+    # multiexp_test.go:95-126 : 73 points, 4 random ones set to infinity, every c agrees
+    G = O.GROUPS[g]
+    n = 73 if g == "bn254_g1" else 24
+    pts, ks = _inputs(G, n, 7, n_inf=4)
+    sm = [G.fr.to_mont(k) for k in ks]
+    expect = O.msm_naive(G, pts, ks)
+    cs = [2, 3, 5, 8, 13, 16] if g == "bn254_g1" else [4, 11]
+    for c in cs:
+        assert O.multi_exp(G, pts, sm, c=c) == expect, c
+
+
+def test_msm_closed_form():
+    # multiexp_test.go:186-216 : 30 points [i]G with scalars i*mixer -> [sum i^2 * mixer]G = [9455*mixer]G
+    G = O.GROUPS["bn254_g1"]
+    pts, ks = _inputs(G, 30, 11)
+    mixer = ks[0]
+    sm = [G.fr.to_mont(k) for k in ks]
+    assert O.multi_exp(G, pts, sm, c=5) == G.scalar_mul(G.gen, (9455 * mixer) % G.fr.q)
+
+
+def test_msm_infinity_and_zero():
+    # multiexp_test.go:128-182
+    G = O.GROUPS["bn254_g1"]
+    n = 20
+    pts, ks = _inputs(G, n, 3)
+    sm = [G.fr.to_mont(k) for k in ks]
+    j = O.inner_msm(G, 4, [G.aff_inf()] * n, sm)
+    assert G.K.is_zero(j[2]) and j == (0, 0, 0)
+    j = O.inner_msm(G, 4, pts, [0] * n)
+    assert j == (0, 0, 0)
+    assert O.inner_msm(G, 5, [], []) == (0, 0, 0)
+
+
+def test_msm_duplicates_and_cancellation():
+    # cross test ingredients multiexp_test.go:233-245: duplicated (point, scalar) pairs force the
+    # doubling branch; P and -P with equal scalars force the cancellation branch.
+    G = O.GROUPS["bn254_g1"]
+    rng = random.Random(5)
+    pts = O.consecutive_multiples(G, 16)
+    ks = [rng.randrange(G.fr.q) for _ in range(16)]
+    pts += pts[:6]
+    ks += ks[:6]
+    pts += [G.aff_neg(p) for p in pts[6:9]]
+    ks += ks[6:9]
+    sm = [G.fr.to_mont(k) for k in ks]
+    expect = O.msm_naive(G, pts, ks)
+    for c in (3, 8, 16):
+        assert O.multi_exp(G, pts, sm, c=c) == expect
+
+
+def test_memory_layout_roundtrip():
+    G = O.GROUPS["bn254_g2"]
+    pts = O.consecutive_multiples(G, 3) + [G.aff_inf()]
+    arr = G.encode_affine(pts)
+    assert arr.shape == (4, 16) and arr.dtype == np.uint64
+    assert not arr[3].any()
+    assert G.decode_affine(arr) == pts
+    G1 = O.GROUPS["bn254_g1"]
+    # generator (1,2) in Montgomery form: X = R mod q  (fp One, ecc/bn254/fp/element.go:195-198)
+    a = G1.encode_affine([G1.gen])
+    assert [int(v) for v in a[0, :4]] == [15230403791020821917, 754611498739239741, 7381016538464732716, 1011752739694698287]
+    ks = [0, 1, G1.fr.q - 1]
+    assert G1.decode_scalars(G1.encode_scalars(ks)) == ks
+
+
+def test_random_scalars_deterministic():
+    fr = O.FIELDS["bn254_fr"]
+    a = O.random_scalars_mont(fr, 50, 0x5EED0001)
+    b = O.random_scalars_mont(fr, 50, 0x5EED0001)
+    assert a == b and all(0 <= v < fr.q for v in a) and len(set(a)) == 50
