@@ -1,0 +1,97 @@
+// Shared host-side declarations of the engine: context, error plumbing, per-group function table.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <mutex>
+
+#include "../../include/gmsm.h"
+#include "groups.cuh"
+
+namespace gmsm {
+
+int set_err(int code, const char* fmt, ...);
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      return ::gmsm::set_err(e_ == cudaErrorMemoryAllocation ? GMSM_ENOMEM                          \
+                     : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? GMSM_ENODEV \
+                                                                                       : GMSM_ECUDA, \
+                     "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));            \
+    }                                                                                              \
+  } while (0)
+
+struct CurveInfo {
+  int coord_words;  // u32 words of one coordinate-field element
+  int fr_bits;
+};
+
+}  // namespace gmsm
+
+struct gmsm_ctx {
+  int curve = 0;
+  int device = 0;
+  size_t max_n = 0;
+  gmsm::CurveInfo ci{};
+  gmsm::WindowPlan plan{};
+  // chunking
+  uint32_t K2 = 16;
+  uint32_t seg_L = 32, seg_S = 0;
+  // device workspace
+  uint32_t* hist = nullptr;      // nb_total + 1 (+pad)
+  uint32_t* offsets = nullptr;   // nb_total + 1
+  uint32_t* block_sums = nullptr;
+  uint32_t* entries = nullptr;   // max_n * W (+pad)
+  void* buckets = nullptr;       // nb_total xyzz
+  void* carries[2] = {nullptr, nullptr};
+  uint32_t* carry_ids[2] = {nullptr, nullptr};
+  void* seg[2] = {nullptr, nullptr};
+  void* win_partials = nullptr;  // W xyzz (own result for single-rank msm)
+  void* fin_scratch = nullptr;   // W xyzz
+  size_t max_chunks = 0;
+  size_t ws_bytes = 0;
+  int last_launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[9] = {};
+  float stage_ms[8] = {};
+  bool have_stage = false;
+  std::mutex mu;
+};
+
+template <class T>
+static inline cudaError_t dmalloc(T** p, size_t bytes, size_t* acc) {
+  *acc += bytes;
+  return cudaMalloc((void**)p, bytes ? bytes : 16);
+}
+
+static inline uint32_t pick_K(size_t n, int nwin) {
+  // chunk length of the accumulate kernel: long enough to amortise the per-chunk bucket search and
+  // flush, short enough to fill 148 SMs x 512 threads several times over
+  double total = (double)n * nwin;
+  double k = total / (148.0 * 512.0 * 8.0);
+  uint32_t K = 4;
+  while (K < 128 && (double)K < k) K <<= 1;
+  return K;
+}
+
+
+namespace gmsm {
+
+static inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+// one table per (curve, group); each lives in its own translation unit (inst_*.cu) so the four
+// heavy template instantiations compile in parallel
+struct GroupVTable {
+  int (*window_sums)(gmsm_ctx*, const void* d_points, const void* d_scalars, size_t n, void* d_partials, cudaStream_t);
+  int (*finalize)(gmsm_ctx*, const void* d_partials, int nranks, void* d_out, cudaStream_t);
+  int (*generate)(const void* d_base, uint64_t start, size_t n, void* d_out, cudaStream_t);
+  void (*test_op_sizes)(int op, int* wa, int* wb, int* wo);
+  int (*test_op)(int op, const uint32_t* da, const uint32_t* db, uint32_t* dout, size_t n);
+  int (*digits_dump)(const void* d_scalars, size_t n, int c, int nwin, uint32_t* dout);
+};
+extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2;
+
+}  // namespace gmsm

@@ -1,0 +1,154 @@
+// Template orchestration of the kernels for one (curve, group); included by inst_*.cu.
+#pragma once
+#include "engine.h"
+#include "kernels.cuh"
+
+namespace gmsm {
+
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+// per-window partial sums -> d_partials (W xyzz)
+template <class G>
+static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scalars, size_t n, void* d_partials,
+                           cudaStream_t st) {
+  using F = typename G::F;
+  using X = XYZZ<F>;
+  const WindowPlan& p = c->plan;
+  int launches = 0;
+  const bool prof = c->profiling;
+  auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], st); };
+  mark(0);
+  if (n == 0) {
+    CK(cudaMemsetAsync(d_partials, 0, (size_t)p.nwin * sizeof(X), st));
+    for (int i = 1; i <= 6; i++) mark(i);
+    c->last_launches = 0;
+    return GMSM_OK;
+  }
+  const uint32_t n32 = (uint32_t)n;
+  const size_t nbp = (size_t)p.nb_total + 1;
+  const auto* scalars = reinterpret_cast<const typename G::Fr*>(d_scalars);
+  const auto* points = reinterpret_cast<const Affine<F>*>(d_points);
+  X* buckets = reinterpret_cast<X*>(c->buckets);
+
+  // K1: digits + histogram
+  CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
+  {
+    unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
+    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->hist);
+    launches++;
+    LAUNCH_CHECK();
+  }
+  mark(1);
+  // K1b: scan
+  {
+    unsigned nb_blocks = nblk(nbp, SCAN_TILE);
+    k_scan_block_sums<<<nb_blocks, SCAN_THREADS, 0, st>>>(c->hist, (uint32_t)nbp, c->block_sums);
+    k_scan_top<<<1, 1024, 0, st>>>(c->block_sums, nb_blocks, c->block_sums + nb_blocks);
+    k_scan_final<<<nb_blocks, SCAN_THREADS, 0, st>>>(c->hist, (uint32_t)nbp, c->block_sums, c->offsets);
+    launches += 3;
+    LAUNCH_CHECK();
+  }
+  mark(2);
+  // K1c: scatter
+  {
+    unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
+    k_digits_scatter<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->hist, c->offsets, c->entries);
+    launches++;
+    LAUNCH_CHECK();
+  }
+  mark(3);
+  // K2: accumulate
+  const uint32_t K = pick_K(n, p.nwin);
+  const size_t nchunks = (n * (size_t)p.nwin + K - 1) / K;
+  if (nchunks > c->max_chunks) return set_err(GMSM_EINVAL, "internal: chunk bound exceeded (%zu > %zu)", nchunks, c->max_chunks);
+  CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
+  {
+    k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
+                                                        buckets, reinterpret_cast<X*>(c->carries[0]), c->carry_ids[0], 0);
+    launches++;
+    LAUNCH_CHECK();
+  }
+  mark(4);
+  // K2b: carry join levels
+  {
+    size_t n_in = nchunks;
+    int cur = 0;
+    while (n_in > 1) {
+      size_t n_out = (n_in + c->K2 - 1) / c->K2;
+      k_carry_level<G><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
+                                                        (uint32_t)n_in, c->K2, buckets,
+                                                        reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
+      launches++;
+      LAUNCH_CHECK();
+      n_in = n_out;
+      cur ^= 1;
+    }
+  }
+  mark(5);
+  // K3: bucket reduction
+  {
+    const uint32_t S = c->seg_S, L = c->seg_L;
+    k_bucket_segments<G><<<nblk((size_t)p.nwin * S, 128), 128, 0, st>>>(buckets, p.nwin, p.nb, p.nb_last, L, S,
+                                                                       reinterpret_cast<X*>(c->seg[0]));
+    launches++;
+    LAUNCH_CHECK();
+    uint32_t per = S;
+    int cur = 0;
+    while (per > 1) {
+      uint32_t R = 16;
+      uint32_t outp = (per + R - 1) / R;
+      X* dst = (outp == 1) ? reinterpret_cast<X*>(d_partials) : reinterpret_cast<X*>(c->seg[cur ^ 1]);
+      k_sum_groups<G><<<nblk((size_t)p.nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
+                                                                       p.nwin, dst);
+      launches++;
+      LAUNCH_CHECK();
+      per = outp;
+      cur ^= 1;
+    }
+    if (S == 1) {
+      CK(cudaMemcpyAsync(d_partials, c->seg[0], (size_t)p.nwin * sizeof(X), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  mark(6);
+  c->last_launches = launches;
+  return GMSM_OK;
+}
+
+template <class G>
+static int run_finalize(gmsm_ctx* c, const void* d_partials, int nranks, void* d_out, cudaStream_t st) {
+  using F = typename G::F;
+  k_finalize<G><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->plan.nwin, c->plan.c,
+                                  reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
+
+template <class G>
+static int run_generate(const void* d_base, uint64_t start, size_t n, void* d_out, cudaStream_t st) {
+  size_t threads = (n + GEN_M - 1) / GEN_M;
+  k_generate_multiples<G><<<nblk(threads, 128), 128, 0, st>>>(reinterpret_cast<const Affine<typename G::F>*>(d_base), start,
+                                                             (uint64_t)n, reinterpret_cast<Affine<typename G::F>*>(d_out));
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
+template <class G>
+static int run_test_op(int op, const uint32_t* da, const uint32_t* db, uint32_t* dout, size_t n) {
+  k_test_op<G><<<nblk(n, 64), 64>>>(op, da, db, dout, (uint32_t)n);
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
+template <class G>
+static int run_digits_dump(const void* d_scalars, size_t n, int c, int nwin, uint32_t* dout) {
+  k_digits_dump<G><<<nblk(n, 128), 128>>>(reinterpret_cast<const typename G::Fr*>(d_scalars), (uint32_t)n, c, nwin, dout);
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
+#define GMSM_INSTANTIATE(G, NAME)                                                                  \
+  const GroupVTable NAME = {&run_window_sums<G>, &run_finalize<G>, &run_generate<G>, &test_op_sizes<G>, \
+                            &run_test_op<G>, &run_digits_dump<G>};
+
+}  // namespace gmsm

@@ -1,0 +1,368 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces (reference, /root/reference):
+//   fp.Mul / Square  : field/asm/element_4w_amd64.s:208-297, element_6w_amd64.s:282-395,
+//                      generic CIOS ecc/bn254/fp/element.go:470-591 (final subtract :583-590)
+//   fp.Add/Double/Sub/Neg : ecc/bn254/fp/element.go:386-454
+//   fr fromMont      : ecc/bn254/fr/element.go:593-642 (via Bits() :855-859)
+//
+// Representation is byte-identical to the reference's [L]uint64 little-endian Montgomery form
+// (value * 2^(64L) mod q, always fully reduced), read as 2L little-endian uint32 limbs.
+//
+// Device multiplication: row-wise CIOS with two accumulators of 64-bit-aligned (lo,hi) pairs --
+// one aligned on even columns, one on odd columns -- so every 32x32+64 multiply-add is one
+// IMAD.WIDE.U32.X (ptxas fuses each mad.lo.cc/madc.hi.cc pair) and the per-row shift by one limb
+// is free: the accumulators swap roles every row and the one becoming odd-aligned is shifted two
+// limbs by reading the MAD addend at index+2.  The low limb never needs a cross-accumulator add: it
+// sums to 0 mod 2^32 after the reduction step and its 1-bit carry is injected as the carry-in of
+// the next row's first chain.  2*N^2/2 = N^2 IMAD.WIDE per product half, 2*N^2 total
+// (N=8: 128, N=12: 288).  Algorithm validated limb-exactly by tools/sim_montmul.py.
+#pragma once
+#include <cstdint>
+
+#include "field_consts.cuh"
+#include "hd.cuh"
+
+namespace gmsm {
+
+#if defined(__CUDA_ARCH__)
+// ---- PTX carry-chain primitives (CC.CF lives across consecutive volatile asm statements) ----
+GMSM_D uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t addc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t subc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+GMSM_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+GMSM_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+GMSM_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+#endif
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  using Params = P;
+  uint32_t l[N];
+
+  GMSM_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = 0;
+    return r;
+  }
+  GMSM_HD static Fp one() {  // R mod q  (SetOne, fp/element.go:194-200)
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+    return r;
+  }
+  GMSM_HD bool is_zero() const {  // fp/element.go:221
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i];
+    return o == 0;
+  }
+  GMSM_HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+    return o == 0;
+  }
+  GMSM_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = (a >= q) ? a - q : a, for a < 2q < 2^(32N)
+template <class P>
+GMSM_HD void fp_reduce_once(Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+#if defined(__CUDA_ARCH__)
+  t[0] = sub_cc(a.l[0], P::mod(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::mod(i));
+  uint32_t borrow = subc(0, 0);  // 0xffffffff if a < q
+#pragma unroll
+  for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+#else
+  uint64_t br = 0;
+  for (int i = 0; i < N; i++) {
+    uint64_t d = (uint64_t)a.l[i] - P::mod(i) - br;
+    t[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  if (!br)
+    for (int i = 0; i < N; i++) a.l[i] = t[i];
+#endif
+}
+
+// fp.Add  (fp/element.go:386-401): a, b < q
+template <class P>
+GMSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+#if defined(__CUDA_ARCH__)
+  r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+  r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);  // q < 2^(32N-1): no carry out
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < N; i++) {
+    c += (uint64_t)a.l[i] + b.l[i];
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  fp_reduce_once(r);
+  return r;
+}
+
+// fp.Double (fp/element.go:403-418)
+template <class P>
+GMSM_HD Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add(a, a);
+}
+
+// fp.Sub (fp/element.go:420-438)
+template <class P>
+GMSM_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  constexpr int N = P::N;
+  Fp<P> r;
+#if defined(__CUDA_ARCH__)
+  r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+  uint32_t mask = subc(0, 0);  // all ones if borrow
+  r.l[0] = add_cc(r.l[0], P::mod(0) & mask);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & mask);
+  r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1) & mask);
+#else
+  uint64_t br = 0;
+  for (int i = 0; i < N; i++) {
+    uint64_t d = (uint64_t)a.l[i] - b.l[i] - br;
+    r.l[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  if (br) {
+    uint64_t c = 0;
+    for (int i = 0; i < N; i++) {
+      c += (uint64_t)r.l[i] + P::mod(i);
+      r.l[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+#endif
+  return r;
+}
+
+// fp.Neg (fp/element.go:440-454): Neg(0) = 0
+template <class P>
+GMSM_HD Fp<P> fp_neg(const Fp<P>& a) {
+  return fp_sub(Fp<P>::zero(), a);
+}
+
+// ------------------------------------------------------------------------------------------
+// Montgomery multiplication  z = x*y*R^-1 mod q   (F1)
+// ------------------------------------------------------------------------------------------
+template <class P>
+GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
+  constexpr int N = P::N;
+  Fp<P> r;
+#if defined(__CUDA_ARCH__) && !defined(GMSM_PORTABLE_MUL)
+  // Two accumulators, N+2 slots each: [0..N-1] limbs, [N] carry limb, [N+1] always zero.
+  uint32_t A[N + 2], B[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
+  uint32_t dprev = 0;  // dangling limb of the previous row (column 0 of the current frame)
+  uint32_t e0prev = 0; // low limb of the previous row's Ev after reduction (e0prev + dprev == 0 mod 2^32)
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Ev = (i & 1) ? B : A;
+    uint32_t* Od = (i & 1) ? A : B;
+    const uint32_t bi = y.l[i];
+    // frame shift from the previous row: the previous Ev is this row's pending Od:
+    //   k  = carry(e0prev + dprev)  -> carry-in of this row's first chain
+    //   d  = prevEv[1] = Od[1]      -> this row's dangling limb (column 0)
+    const uint32_t d = (i == 0) ? 0u : Od[1];
+    // step 1: Ev += x_even * bi
+    if (i == 0) {
+      Ev[0] = mad_lo_cc(x.l[0], bi, Ev[0]);
+    } else {
+      (void)add_cc(e0prev, dprev);
+      Ev[0] = madc_lo_cc(x.l[0], bi, Ev[0]);
+    }
+    Ev[1] = madc_hi_cc(x.l[0], bi, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(x.l[j], bi, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(x.l[j], bi, Ev[j + 1]);
+    }
+    Ev[N] = addc(0, 0);
+    // step 2: Od = (Od >> 2 limbs) + x_odd * bi   (no carry out; Od[N+1] == 0)
+    Od[0] = mad_lo_cc(x.l[1], bi, Od[2]);
+    Od[1] = madc_hi_cc(x.l[1], bi, Od[3]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(x.l[j + 1], bi, Od[j + 2]);
+      Od[j + 1] = madc_hi_cc(x.l[j + 1], bi, Od[j + 3]);
+    }
+    Od[N] = 0;  // stale carry limb consumed by the shift
+    // step 3
+    const uint32_t m = (Ev[0] + d) * P::INV;
+    // step 4: Ev += q_even * m
+    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    // step 5: Od += q_odd * m  (no carry out)
+    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
+    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+    }
+    e0prev = Ev[0];
+    dprev = d;
+  }
+  // After the last row (N even): last Ev = B, last Od = A.
+  //   result = A[0..N-1] + B[1] + carry(B[0] + dprev) + 2^32 * B[2..N]
+  (void)add_cc(e0prev, dprev);
+  r.l[0] = addc_cc(A[0], B[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(A[i], B[i + 1]);
+  r.l[N - 1] = addc(A[N - 1], B[N]);
+  fp_reduce_once(r);
+#else
+  // portable CIOS on 32-bit limbs (same recurrence as fp/element.go:470-591 at half the word size)
+  uint32_t t[N + 2];
+  for (int i = 0; i < N + 2; i++) t[i] = 0;
+  for (int i = 0; i < N; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < N; j++) {
+      c += (uint64_t)x.l[j] * y.l[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[N];
+    t[N] = (uint32_t)c;
+    t[N + 1] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * P::INV;
+    c = (uint64_t)m * P::mod(0) + t[0];
+    c >>= 32;
+    for (int j = 1; j < N; j++) {
+      c += (uint64_t)m * P::mod(j) + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[N];
+    t[N - 1] = (uint32_t)c;
+    t[N] = t[N + 1] + (uint32_t)(c >> 32);
+  }
+  for (int i = 0; i < N; i++) r.l[i] = t[i];
+  fp_reduce_once(r);
+#endif
+  return r;
+}
+
+template <class P>
+GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {
+  return fp_mul(x, x);
+}
+
+// Montgomery -> canonical: multiply by 1 (fromMont, fr/element.go:593-642)
+template <class P>
+GMSM_HD Fp<P> fp_from_mont(const Fp<P>& x) {
+  Fp<P> o = Fp<P>::zero();
+  o.l[0] = 1;
+  return fp_mul(x, o);
+}
+
+// canonical -> Montgomery (toMont, fp/element.go:782-784)
+template <class P>
+GMSM_HD Fp<P> fp_to_mont(const Fp<P>& x) {
+  Fp<P> r2;
+#pragma unroll
+  for (int i = 0; i < P::N; i++) r2.l[i] = P::r2(i);
+  return fp_mul(x, r2);
+}
+
+// x^-1 by Fermat (x^(q-2)); Inverse(0) = 0 like fp/element.go:1170-1172.  Any correct inversion
+// is limb-identical to the reference's Pornin GCD since the reduced Montgomery value is unique.
+// Only used once per MSM (final normalisation) and in batched-inversion kernels.
+template <class P>
+GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
+  constexpr int N = P::N;
+  // exponent e = q - 2
+  uint32_t e[N];
+  {
+    uint64_t br = 2;
+    for (int i = 0; i < N; i++) {
+      uint64_t d = (uint64_t)P::mod(i) - br;
+      e[i] = (uint32_t)d;
+      br = (d >> 32) & 1;
+    }
+  }
+  Fp<P> acc = Fp<P>::one();
+  bool started = false;
+  for (int i = 32 * N - 1; i >= 0; i--) {
+    if (started) acc = fp_sqr(acc);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      acc = started ? fp_mul(acc, x) : x;
+      started = true;
+    }
+  }
+  return acc;
+}
+
+// uniform coordinate-field interface (overloaded for Fp2 in fp2.cuh)
+template <class P> GMSM_HD Fp<P> f_add(const Fp<P>& a, const Fp<P>& b) { return fp_add(a, b); }
+template <class P> GMSM_HD Fp<P> f_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
+template <class P> GMSM_HD Fp<P> f_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
+template <class P> GMSM_HD Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
+template <class P> GMSM_HD Fp<P> f_dbl(const Fp<P>& a) { return fp_dbl(a); }
+template <class P> GMSM_HD Fp<P> f_neg(const Fp<P>& a) { return fp_neg(a); }
+template <class P> GMSM_HD Fp<P> f_inv(const Fp<P>& a) { return fp_inv(a); }
+
+}  // namespace gmsm

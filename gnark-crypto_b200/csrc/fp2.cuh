@@ -1,0 +1,62 @@
+// Quadratic extension Fp2 = Fp[u]/(u^2+1) for G2 (both bn254 and bls12-381 use u^2 = -1).
+//
+// Replaces (reference): E2.Mul/Square ecc/bn254/internal/fptower/e2_bn254.go:28-51 (asm
+// e2_amd64.s:393,548), Add/Sub/Double/Neg e2.go:104-126, Inverse e2_bn254.go:61-73; identical
+// formulas ecc/bls12-381/internal/fptower/e2_bls381.go:16-74.  Memory order A0, A1 (e2.go:14-16).
+#pragma once
+#include "field.cuh"
+
+namespace gmsm {
+
+template <class P>
+struct Fp2 {
+  using Params = P;
+  static constexpr int N = 2 * P::N;  // 32-bit words in memory
+  Fp<P> a0, a1;
+  GMSM_HD static Fp2 zero() { return Fp2{Fp<P>::zero(), Fp<P>::zero()}; }
+  GMSM_HD static Fp2 one() { return Fp2{Fp<P>::one(), Fp<P>::zero()}; }
+  GMSM_HD bool is_zero() const { return a0.is_zero() && a1.is_zero(); }
+  GMSM_HD bool operator==(const Fp2& b) const { return a0 == b.a0 && a1 == b.a1; }
+  GMSM_HD bool operator!=(const Fp2& b) const { return !(*this == b); }
+};
+
+template <class P> GMSM_HD Fp2<P> f_add(const Fp2<P>& a, const Fp2<P>& b) { return Fp2<P>{fp_add(a.a0, b.a0), fp_add(a.a1, b.a1)}; }
+template <class P> GMSM_HD Fp2<P> f_sub(const Fp2<P>& a, const Fp2<P>& b) { return Fp2<P>{fp_sub(a.a0, b.a0), fp_sub(a.a1, b.a1)}; }
+template <class P> GMSM_HD Fp2<P> f_dbl(const Fp2<P>& a) { return Fp2<P>{fp_dbl(a.a0), fp_dbl(a.a1)}; }
+template <class P> GMSM_HD Fp2<P> f_neg(const Fp2<P>& a) { return Fp2<P>{fp_neg(a.a0), fp_neg(a.a1)}; }
+
+// Karatsuba, 3 fp.Mul (e2_bn254.go:28-38)
+template <class P>
+GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
+  Fp<P> a = fp_add(x.a0, x.a1);
+  Fp<P> b = fp_add(y.a0, y.a1);
+  a = fp_mul(a, b);
+  b = fp_mul(x.a0, y.a0);
+  Fp<P> c = fp_mul(x.a1, y.a1);
+  Fp2<P> z;
+  z.a1 = fp_sub(fp_sub(a, b), c);
+  z.a0 = fp_sub(b, c);
+  return z;
+}
+
+// 2 fp.Mul (e2_bn254.go:41-51)
+template <class P>
+GMSM_HD Fp2<P> f_sqr(const Fp2<P>& x) {
+  Fp<P> a = fp_add(x.a0, x.a1);
+  Fp<P> b = fp_sub(x.a0, x.a1);
+  a = fp_mul(a, b);
+  b = fp_dbl(fp_mul(x.a0, x.a1));
+  return Fp2<P>{a, b};
+}
+
+// (a0 - a1 u) / (a0^2 + a1^2)   (e2_bn254.go:61-73)
+template <class P>
+GMSM_HD Fp2<P> f_inv(const Fp2<P>& x) {
+  Fp<P> t0 = fp_sqr(x.a0);
+  Fp<P> t1 = fp_sqr(x.a1);
+  t0 = fp_add(t0, t1);
+  t1 = fp_inv(t0);
+  return Fp2<P>{fp_mul(x.a0, t1), fp_neg(fp_mul(x.a1, t1))};
+}
+
+}  // namespace gmsm

@@ -1,0 +1,433 @@
+// Host orchestration + C ABI (include/gmsm.h) of the B200 MSM engine.
+// There is deliberately no CPU fallback: every entry point fails with GMSM_ENODEV / GMSM_ECUDA when
+// the device path is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+using namespace gmsm;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+int gmsm::set_err(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+extern "C" const char* gmsm_last_error(void) { return g_err.c_str(); }
+extern "C" const char* gmsm_version(void) { return "gmsm-b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// per-curve dispatch
+// ------------------------------------------------------------------------------------------
+static bool curve_info(int curve, CurveInfo* ci) {
+  switch (curve) {
+    case GMSM_BN254_G1: *ci = {bn254_g1::F::N, bn254_fr::BITS}; return true;
+    case GMSM_BN254_G2: *ci = {bn254_g2::F::N, bn254_fr::BITS}; return true;
+    case GMSM_BLS12381_G1: *ci = {bls12381_g1::F::N, bls12381_fr::BITS}; return true;
+    case GMSM_BLS12381_G2: *ci = {bls12381_g2::F::N, bls12381_fr::BITS}; return true;
+  }
+  return false;
+}
+
+extern "C" size_t gmsm_affine_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 8u * ci.coord_words : 0; }
+extern "C" size_t gmsm_scalar_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 32u : 0; }
+extern "C" size_t gmsm_jac_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 12u * ci.coord_words : 0; }
+extern "C" size_t gmsm_xyzz_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 16u * ci.coord_words : 0; }
+
+static const GroupVTable* vtable(int curve) {
+  switch (curve) {
+    case GMSM_BN254_G1: return &vt_bn254_g1;
+    case GMSM_BN254_G2: return &vt_bn254_g2;
+    case GMSM_BLS12381_G1: return &vt_bls12381_g1;
+    case GMSM_BLS12381_G2: return &vt_bls12381_g2;
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// window-width model.  Cost in "mixed-add equivalents":
+//   accumulate: W * n            (one mixed add per non-zero digit)
+//   reduce    : nb_total * (2 full adds + scalar-mul/L) * 1.4  (full add ~ 1.4 mixed adds), at
+//               the lower parallel efficiency of the short reduce kernels (x RED_PENALTY)
+// constants calibrated on B200; c can be forced through gmsm_ctx_create / GMSM_C.
+// ------------------------------------------------------------------------------------------
+static int choose_c(int fr_bits, size_t n) {
+  if (const char* e = getenv("GMSM_C")) {
+    int c = atoi(e);
+    if (c >= 2 && c <= 24) return c;
+  }
+  double best = 1e300;
+  int bc = 8;
+  for (int c = 4; c <= 22; c++) {
+    WindowPlan p = make_plan(fr_bits, c);
+    double acc = (double)p.nwin * (double)n;
+    double red = (double)p.nb_total * (2.0 + 22.0 / 32.0) * 1.4 * 3.0;
+    double sort_cost = (double)p.nwin * (double)n * 0.02;
+    double cost = acc + red + sort_cost;
+    if (cost < best) { best = cost; bc = c; }
+  }
+  return bc;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static int ctx_alloc(gmsm_ctx* c) {
+  const WindowPlan& p = c->plan;
+  const size_t xyzz = 16u * c->ci.coord_words;
+  size_t acc = 0;
+  const size_t nbp = (size_t)p.nb_total + 1;
+  CK(dmalloc(&c->hist, (nbp + 8) * 4, &acc));
+  CK(dmalloc(&c->offsets, (nbp + 8) * 4, &acc));
+  CK(dmalloc(&c->block_sums, ((nbp + SCAN_TILE - 1) / SCAN_TILE + 8) * 4, &acc));
+  const size_t ent = c->max_n * (size_t)p.nwin;
+  CK(dmalloc(&c->entries, (ent + 16) * 4, &acc));
+  CK(dmalloc(&c->buckets, (size_t)p.nb_total * xyzz, &acc));
+  // chunks(n) = ceil(n*W / K(n)) <= max(148*512*8 (+slack), ceil(max_n*W/128))  -- see pick_K
+  size_t mc = std::max<size_t>(700000, (ent + 127) / 128 + 1);
+  c->max_chunks = mc;
+  CK(dmalloc(&c->carries[0], mc * xyzz, &acc));
+  CK(dmalloc(&c->carry_ids[0], (mc + 8) * 4, &acc));
+  size_t mc2 = (mc + c->K2 - 1) / c->K2;
+  CK(dmalloc(&c->carries[1], mc2 * xyzz, &acc));
+  CK(dmalloc(&c->carry_ids[1], (mc2 + 8) * 4, &acc));
+  uint32_t nbmax = std::max(p.nb, p.nb_last);
+  c->seg_L = 32;
+  c->seg_S = (nbmax + c->seg_L - 1) / c->seg_L;
+  CK(dmalloc(&c->seg[0], (size_t)p.nwin * c->seg_S * xyzz, &acc));
+  CK(dmalloc(&c->seg[1], (size_t)p.nwin * ((c->seg_S + 15) / 16) * xyzz, &acc));
+  CK(dmalloc(&c->win_partials, (size_t)p.nwin * xyzz, &acc));
+  CK(dmalloc(&c->fin_scratch, (size_t)p.nwin * xyzz, &acc));
+  c->ws_bytes = acc;
+  for (int i = 0; i < 9; i++) CK(cudaEventCreate(&c->ev[i]));
+  return GMSM_OK;
+}
+
+static void ctx_free(gmsm_ctx* c) {
+  cudaSetDevice(c->device);
+  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->buckets);
+  for (int i = 0; i < 2; i++) { cudaFree(c->carries[i]); cudaFree(c->carry_ids[i]); cudaFree(c->seg[i]); }
+  cudaFree(c->win_partials); cudaFree(c->fin_scratch);
+  for (int i = 0; i < 9; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+}
+
+extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, int device) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
+  if (c != 0 && (c < 2 || c > 24)) { set_err(GMSM_EINVAL, "window width c=%d out of range [2,24]", c); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
+  if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_err(GMSM_ECUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+  if (max_n == 0) max_n = 1;
+  gmsm_ctx* ctx = new gmsm_ctx();
+  ctx->curve = curve;
+  ctx->device = device;
+  ctx->max_n = max_n;
+  ctx->ci = ci;
+  if (c == 0) c = choose_c(ci.fr_bits, max_n);
+  ctx->plan = make_plan(ci.fr_bits, c);
+  if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
+    set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 32-bit entry index; shard the MSM", max_n, ctx->plan.nwin);
+    delete ctx;
+    return nullptr;
+  }
+  if (max_n > (1ull << 31) - 1) { set_err(GMSM_EINVAL, "n too large"); delete ctx; return nullptr; }
+  if (ctx_alloc(ctx) != GMSM_OK) { ctx_free(ctx); delete ctx; return nullptr; }
+  return ctx;
+}
+
+extern "C" void gmsm_ctx_destroy(gmsm_ctx_t* ctx) {
+  if (!ctx) return;
+  ctx_free(ctx);
+  delete ctx;
+}
+extern "C" int gmsm_ctx_window_bits(const gmsm_ctx_t* ctx) { return ctx ? ctx->plan.c : 0; }
+extern "C" int gmsm_ctx_num_windows(const gmsm_ctx_t* ctx) { return ctx ? ctx->plan.nwin : 0; }
+extern "C" size_t gmsm_ctx_workspace_bytes(const gmsm_ctx_t* ctx) { return ctx ? ctx->ws_bytes : 0; }
+extern "C" int gmsm_ctx_last_launches(const gmsm_ctx_t* ctx) { return ctx ? ctx->last_launches : 0; }
+extern "C" void gmsm_ctx_set_profiling(gmsm_ctx_t* ctx, int on) { if (ctx) ctx->profiling = on != 0; }
+extern "C" int gmsm_ctx_last_stage_ms(gmsm_ctx_t* ctx, float out_ms[8]) {
+  if (!ctx || !ctx->have_stage) return set_err(GMSM_EINVAL, "no profiled call recorded");
+  cudaSetDevice(ctx->device);
+  CK(cudaEventSynchronize(ctx->ev[8]));
+  float tot = 0;
+  for (int i = 0; i < 7; i++) {
+    CK(cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  }
+  CK(cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[7]));
+  out_ms[7] = tot;
+  return GMSM_OK;
+}
+
+extern "C" int gmsm_ctx_window_sums_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
+                                           void* d_partials, void* stream) {
+  if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  int rc = GMSM_OK;
+  rc = vtable(ctx->curve)->window_sums(ctx, d_points, d_scalars, n, d_partials, (cudaStream_t)stream);
+  if (rc == GMSM_OK && ctx->profiling) {
+    cudaEventRecord(ctx->ev[7], (cudaStream_t)stream);
+    cudaEventRecord(ctx->ev[8], (cudaStream_t)stream);
+    ctx->have_stage = true;
+  }
+  return rc;
+}
+
+extern "C" int gmsm_ctx_finalize_device(gmsm_ctx_t* ctx, const void* d_partials, int nranks, void* d_out_jac,
+                                        void* stream) {
+  if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (nranks < 1) return set_err(GMSM_EINVAL, "nranks must be >= 1");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  int rc = GMSM_OK;
+  rc = vtable(ctx->curve)->finalize(ctx, d_partials, nranks, d_out_jac, (cudaStream_t)stream);
+  return rc;
+}
+
+extern "C" int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
+                                   void* d_out_jac, void* stream) {
+  if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  int rc = GMSM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = vtable(ctx->curve)->window_sums(ctx, d_points, d_scalars, n, ctx->win_partials, st);
+  if (rc != GMSM_OK) return rc;
+  rc = vtable(ctx->curve)->finalize(ctx, ctx->win_partials, 1, d_out_jac, st);
+  if (rc != GMSM_OK) return rc;
+  ctx->last_launches += 1;
+  if (ctx->profiling) {
+    cudaEventRecord(ctx->ev[7], st);
+    cudaEventRecord(ctx->ev[8], st);
+    ctx->have_stage = true;
+  }
+  return GMSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// resident bases + one-shot host API
+// ------------------------------------------------------------------------------------------
+struct gmsm_bases {
+  int curve;
+  int device;
+  size_t n;
+  size_t cap = 0;
+  void* d_points;
+  // per-bases engine state (lazy): scalar staging + ctx sized for the largest request so far
+  gmsm_ctx* ctx = nullptr;
+  void* d_scalars = nullptr;
+  size_t scalars_cap = 0;
+  void* d_out = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+};
+
+static int check_nb_tasks(int nb_tasks) {
+  // (*G1Jac).MultiExp, multiexp.go:67-71
+  if (nb_tasks > 1024) return set_err(GMSM_EINVAL, "invalid config: config.NbTasks > 1024");
+  return GMSM_OK;
+}
+
+extern "C" void gmsm_bases_free(gmsm_bases_t* b);
+
+// allocate an (empty) resident-bases object with room for `cap` points
+static gmsm_bases* bases_alloc(int curve, size_t cap, int device) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
+  if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range", device); return nullptr; }
+  cudaSetDevice(device);
+  gmsm_bases* b = new gmsm_bases();
+  b->curve = curve; b->device = device; b->n = 0; b->cap = cap;
+  size_t bytes = cap * 8u * ci.coord_words;
+  if (cudaMalloc(&b->d_points, bytes ? bytes : 16) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc(%zu) for bases failed", bytes); delete b; return nullptr; }
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(GMSM_ECUDA, "stream create failed"); cudaFree(b->d_points); delete b; return nullptr; }
+  if (cudaMalloc(&b->d_out, 12u * ci.coord_words) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc out"); cudaFree(b->d_points); cudaStreamDestroy(b->stream); delete b; return nullptr; }
+  return b;
+}
+
+// asynchronous H2D of n points into the object (ordered on its stream before the next multiexp)
+static int bases_fill(gmsm_bases* b, const uint64_t* points, size_t n) {
+  CurveInfo ci;
+  curve_info(b->curve, &ci);
+  if (n > b->cap) return set_err(GMSM_EINVAL, "internal: bases capacity");
+  CK(cudaSetDevice(b->device));
+  if (n) CK(cudaMemcpyAsync(b->d_points, points, n * 8u * ci.coord_words, cudaMemcpyHostToDevice, b->stream));
+  b->n = n;
+  return GMSM_OK;
+}
+
+extern "C" gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size_t n, int device) {
+  gmsm_bases* b = bases_alloc(curve, n, device);
+  if (!b) return nullptr;
+  if (bases_fill(b, points, n) != GMSM_OK || cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    std::string keep = g_err.empty() ? std::string("H2D copy of bases failed") : g_err;
+    gmsm_bases_free(b);
+    g_err = keep;
+    return nullptr;
+  }
+  return b;
+}
+
+extern "C" void gmsm_bases_free(gmsm_bases_t* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->ctx) gmsm_ctx_destroy(b->ctx);
+  cudaFree(b->d_points); cudaFree(b->d_scalars); cudaFree(b->d_out);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_t* scalars, size_t n, int nb_tasks,
+                                   uint64_t* out_jac) {
+  if (!b) return set_err(GMSM_EINVAL, "null bases");
+  if (int rc = check_nb_tasks(nb_tasks)) return rc;
+  if (offset > b->n || n > b->n - offset) return set_err(GMSM_EINVAL, "len(points) != len(scalars)");
+  std::lock_guard<std::mutex> lk(b->mu);
+  CK(cudaSetDevice(b->device));
+  CurveInfo ci;
+  curve_info(b->curve, &ci);
+  const size_t jac_bytes = 12u * ci.coord_words;
+  if (n == 0) { memset(out_jac, 0, jac_bytes); return GMSM_OK; }
+  // engine sized to the request (window width depends on n); re-created when n grows or shrinks 4x
+  if (!b->ctx || b->ctx->max_n < n || b->ctx->max_n > 4 * n) {
+    if (b->ctx) { gmsm_ctx_destroy(b->ctx); b->ctx = nullptr; }
+    b->ctx = gmsm_ctx_create((gmsm_curve_t)b->curve, n, 0, b->device);
+    if (!b->ctx) return GMSM_ECUDA;
+  }
+  if (b->scalars_cap < n) {
+    cudaFree(b->d_scalars); b->d_scalars = nullptr; b->scalars_cap = 0;
+    CK(cudaMalloc(&b->d_scalars, n * 32));
+    b->scalars_cap = n;
+  }
+  CK(cudaMemcpyAsync(b->d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, b->stream));
+  const char* pts = reinterpret_cast<const char*>(b->d_points) + offset * 8u * ci.coord_words;
+  int rc = gmsm_ctx_msm_device(b->ctx, pts, b->d_scalars, n, b->d_out, b->stream);
+  if (rc != GMSM_OK) return rc;
+  CK(cudaMemcpyAsync(out_jac, b->d_out, jac_bytes, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return GMSM_OK;
+}
+
+extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                             uint64_t* out_jac) {
+  if (int rc = check_nb_tasks(nb_tasks)) return rc;
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  if (n == 0) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    memset(out_jac, 0, 12u * ci.coord_words);
+    return GMSM_OK;
+  }
+  int device = 0;
+  if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
+  // per-(curve, device) session: device buffers and the engine context are kept between calls
+  // (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
+  static std::mutex sess_mu;
+  static std::map<std::pair<int, int>, gmsm_bases*> sessions;
+  std::lock_guard<std::mutex> lk(sess_mu);
+  gmsm_bases*& sb = sessions[std::make_pair((int)curve, device)];
+  if (sb && (sb->cap < n || sb->cap > 4 * n + 1024)) { gmsm_bases_free(sb); sb = nullptr; }
+  if (!sb) {
+    sb = bases_alloc(curve, n, device);
+    if (!sb) return g_err.find("no CUDA device") != std::string::npos ? GMSM_ENODEV : GMSM_ECUDA;
+  }
+  if (int rc = bases_fill(sb, points, n)) return rc;
+  return gmsm_bases_multiexp(sb, 0, scalars, n, nb_tasks, out_jac);
+}
+
+extern "C" int gmsm_bn254_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_BN254_G1, p, s, n, t, out); }
+extern "C" int gmsm_bn254_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[24]) { return gmsm_multiexp(GMSM_BN254_G2, p, s, n, t, out); }
+extern "C" int gmsm_bls12381_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[18]) { return gmsm_multiexp(GMSM_BLS12381_G1, p, s, n, t, out); }
+extern "C" int gmsm_bls12381_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BLS12381_G2, p, s, n, t, out); }
+
+// ------------------------------------------------------------------------------------------
+// base generator
+// ------------------------------------------------------------------------------------------
+extern "C" int gmsm_generate_multiples_device(gmsm_curve_t curve, const uint64_t* base_affine_host, uint64_t start, size_t n,
+                                              void* d_out_points, void* stream) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  if (n == 0) return GMSM_OK;
+  void* d_base = nullptr;
+  const size_t ab = 8u * ci.coord_words;
+  CK(cudaMalloc(&d_base, ab));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(d_base, base_affine_host, ab, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFree(d_base); return set_err(GMSM_ECUDA, "H2D base: %s", cudaGetErrorString(e)); }
+  int rc = vtable(curve)->generate(d_base, start, n, d_out_points, st);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_base);
+  if (e != cudaSuccess) return set_err(GMSM_ECUDA, "generate_multiples: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------
+extern "C" int gmsm_test_op(gmsm_curve_t curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  int wa = 0, wb = 0, wo = 0;
+  const GroupVTable* vt = vtable(curve);
+  if (!vt) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  vt->test_op_sizes(op, &wa, &wb, &wo);
+  if (wo == 0) return set_err(GMSM_EINVAL, "unknown op %d", op);
+  if (n == 0) return GMSM_OK;
+  uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&da, n * wa * 4));
+  CK(cudaMalloc(&db, n * std::max(wb, 1) * 4));
+  CK(cudaMalloc(&dout, n * wo * 4));
+  CK(cudaMemcpy(da, a, n * wa * 4, cudaMemcpyHostToDevice));
+  if (wb) CK(cudaMemcpy(db, b, n * wb * 4, cudaMemcpyHostToDevice));
+  if (int rc = vt->test_op(op, da, db, dout, n)) return rc;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, n * wo * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return GMSM_OK;
+}
+
+extern "C" int gmsm_test_digits(gmsm_curve_t curve, int c, const uint64_t* scalars, size_t n, uint32_t* out) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  if (c < 2 || c > 24) return set_err(GMSM_EINVAL, "c out of range");
+  if (n == 0) return GMSM_OK;
+  WindowPlan p = make_plan(ci.fr_bits, c);
+  void* ds = nullptr;
+  uint32_t* dout = nullptr;
+  CK(cudaMalloc(&ds, n * 32));
+  CK(cudaMalloc(&dout, n * (size_t)p.nwin * 4));
+  CK(cudaMemcpy(ds, scalars, n * 32, cudaMemcpyHostToDevice));
+  if (int rc = vtable(curve)->digits_dump(ds, n, p.c, p.nwin, dout)) return rc;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, n * (size_t)p.nwin * 4, cudaMemcpyDeviceToHost));
+  cudaFree(ds); cudaFree(dout);
+  return GMSM_OK;
+}

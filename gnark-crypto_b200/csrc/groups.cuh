@@ -1,0 +1,66 @@
+// The four (curve, group) instantiations on the MultiExp path and their memory sizes.
+//   bn254 G1 / G2       ecc/bn254/g1.go:18-30, g2.go:19-31, fr = ecc/bn254/fr (254 bits)
+//   bls12-381 G1 / G2   ecc/bls12-381/g1.go, g2.go, fr = ecc/bls12-381/fr (255 bits)
+#pragma once
+#include "curve.cuh"
+
+namespace gmsm {
+
+template <int ID_, class FP, class FR, bool G2>
+struct GroupT;
+
+template <int ID_, class FP, class FR>
+struct GroupT<ID_, FP, FR, false> {
+  static constexpr int ID = ID_;
+  using F = Fp<FP>;
+  using Fr = Fp<FR>;
+  using FrParams = FR;
+};
+template <int ID_, class FP, class FR>
+struct GroupT<ID_, FP, FR, true> {
+  static constexpr int ID = ID_;
+  using F = Fp2<FP>;
+  using Fr = Fp<FR>;
+  using FrParams = FR;
+};
+
+// ids are the C-ABI's gmsm_curve_t values (include/gmsm.h)
+using bn254_g1 = GroupT<0, bn254_fp, bn254_fr, false>;
+using bn254_g2 = GroupT<1, bn254_fp, bn254_fr, true>;
+using bls12381_g1 = GroupT<2, bls12381_fp, bls12381_fr, false>;
+using bls12381_g2 = GroupT<3, bls12381_fp, bls12381_fr, true>;
+
+// word (u32) counts
+template <class G> constexpr int coord_words() { return G::F::N; }
+template <class G> constexpr int affine_words() { return 2 * G::F::N; }
+template <class G> constexpr int xyzz_words() { return 4 * G::F::N; }
+template <class G> constexpr int jac_words() { return 3 * G::F::N; }
+
+// scan tiling (k_scan_* in kernels.cuh; the host sizes block_sums with it)
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 8;                              // per thread
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;       // per block
+
+// ---- window plan (computeNbChunks / lastC, ecc/bn254/multiexp.go:681-693) ----
+struct WindowPlan {
+  int c;          // window width in bits
+  int nwin;       // W = ceil(fr.Bits / c)
+  int last_c;     // lastC(c)
+  uint32_t nb;    // buckets of a regular window: 2^(c-1)
+  uint32_t nb_last;   // buckets of the last window: 2^(last_c-1)
+  uint32_t nb_total;  // (W-1)*nb + nb_last
+};
+
+inline WindowPlan make_plan(int fr_bits, int c) {
+  WindowPlan p;
+  p.c = c;
+  p.nwin = (fr_bits + c - 1) / c;
+  int avail = p.nwin * c - fr_bits;
+  p.last_c = c + 1 - avail;
+  p.nb = 1u << (c - 1);
+  p.nb_last = 1u << (p.last_c - 1);
+  p.nb_total = (uint32_t)(p.nwin - 1) * p.nb + p.nb_last;
+  return p;
+}
+
+}  // namespace gmsm

@@ -1,0 +1,33 @@
+// CPU build of the arithmetic headers (portable C++ path of field.cuh) for formula tests without a GPU.
+// NOT part of the product library: libgmsm.so never links this file and has no CPU path.  Built by
+// tests/test_hostcheck.py with g++ into build/libgmsm_hostcheck.so.
+#include <cstddef>
+#include <cstdint>
+
+#include "testops.cuh"
+
+using namespace gmsm;
+
+template <class G>
+static int run(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
+  int wa, wb, wo;
+  test_op_sizes<G>(op, &wa, &wb, &wo);
+  if (wo == 0) return 1;
+  for (size_t i = 0; i < n; i++) test_op_one<G>(op, a + i * wa, b + i * wb, o + i * wo);
+  return 0;
+}
+
+extern "C" int hostcheck_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
+  switch (curve) {
+    case 0: return run<bn254_g1>(op, a, b, o, n);
+    case 1: return run<bn254_g2>(op, a, b, o, n);
+    case 2: return run<bls12381_g1>(op, a, b, o, n);
+    case 3: return run<bls12381_g2>(op, a, b, o, n);
+  }
+  return 1;
+}
+
+extern "C" void hostcheck_plan(int fr_bits, int c, int* out6) {
+  WindowPlan p = make_plan(fr_bits, c);
+  out6[0] = p.c; out6[1] = p.nwin; out6[2] = p.last_c; out6[3] = (int)p.nb; out6[4] = (int)p.nb_last; out6[5] = (int)p.nb_total;
+}

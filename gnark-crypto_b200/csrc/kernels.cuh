@@ -1,0 +1,527 @@
+// sm_100a kernels of the Pippenger bucket method.  One template instantiation per (curve, group).
+//
+// Pipeline (replaces ecc/bn254/multiexp.go:148-209 `_innerMsmG1` and its callees):
+//   K1  k_digits_hist      partitionScalars (multiexp.go:709-803) fused with a bucket histogram
+//   K1b k_scan_*           exclusive scan of the histogram -> bucket offsets
+//   K1c k_digits_scatter   partitionScalars again (recomputed, not stored) -> entries grouped by bucket
+//   K2  k_accumulate       bucket accumulation (processChunk, multiexp_jacobian.go:20-39) as a
+//                          load-balanced segmented reduction over the bucket-ordered entry list
+//   K2b k_carry_level      joins partial sums of buckets that span several chunks
+//   K3  k_bucket_segments  bucket reduction sum (k+1)*B[k] (multiexp_jacobian.go:44-52), parallel form
+//       k_sum_groups       tree sum of segment results -> one partial per window
+//   K4  k_finalize         sum over ranks, Horner over windows (msmReduceChunk, multiexp.go:302-315),
+//                          xyzz -> Jacobian -> affine normal form (g1.go:726-731, 150-166)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "groups.cuh"
+#include "testops.cuh"
+
+namespace gmsm {
+
+static constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------------------------------
+// vector load / store of PODs made of uint32 limbs (size multiple of 16 B, 16 B aligned in memory)
+// ------------------------------------------------------------------------------------------
+template <class T>
+GMSM_D T load_vec(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T r;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
+    uint4 v = s[i];
+    w[4 * i + 0] = v.x;
+    w[4 * i + 1] = v.y;
+    w[4 * i + 2] = v.z;
+    w[4 * i + 3] = v.w;
+  }
+  return r;
+}
+template <class T>
+GMSM_D T load_vec_ro(const T* p) {  // read-only path (points are never written during an MSM)
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T r;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
+    uint4 v = __ldg(s + i);
+    w[4 * i + 0] = v.x;
+    w[4 * i + 1] = v.y;
+    w[4 * i + 2] = v.z;
+    w[4 * i + 3] = v.w;
+  }
+  return r;
+}
+template <class T>
+GMSM_D void store_vec(T* p, const T& r) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+  uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// out-of-line copies of the rare / cold group operations keep the hot loops small (one mixed add is
+// ~2k SASS instructions; the instruction cache is 32 KB L1.5)
+template <class F>
+__device__ __noinline__ void xyzz_add_cold(XYZZ<F>& p, const XYZZ<F>& q) {
+  xyzz_add(p, q);
+}
+template <class F>
+__device__ __noinline__ XYZZ<F> xyzz_double_cold(const XYZZ<F>& q) {
+  return xyzz_double(q);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: signed-digit recoding.  Calls fn(window, magnitude >= 1, sign) for every non-zero digit.
+// Semantics of partitionScalars (multiexp.go:743-800): zero scalars skipped; digit = carry + c bits;
+// windows 0..W-2 borrow (digit > 2^(c-1)-1 -> digit -= 2^c, carry 1); last window never borrows.
+// ------------------------------------------------------------------------------------------
+template <class G, class Fn>
+GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn) {
+  using Fr = typename G::Fr;
+  constexpr int N = Fr::N;
+  if (s_mont.is_zero()) return;           // IsZero() on the Montgomery limbs, multiexp.go:743
+  Fr k = fp_from_mont(s_mont);            // Bits(), fr/element.go:855-859
+  uint32_t v[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = k.l[i];
+  const uint32_t mask = (1u << c) - 1u;
+  const uint32_t maxd = (1u << (c - 1)) - 1u;
+  uint32_t carry = 0;
+  for (int j = 0; j < nwin; j++) {
+    uint32_t d = (v[0] & mask) + carry;
+    // 256-bit (384-bit) logical shift right by c (c < 32)
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) v[i] = __funnelshift_r(v[i], v[i + 1], c);
+    v[N - 1] >>= c;
+    if (j < nwin - 1) {
+      carry = 0;
+      if (d > maxd) {
+        // negative digit: d - 2^c; magnitude 2^c - d
+        uint32_t mag = (1u << c) - d;
+        carry = 1;
+        fn(j, mag, 1u);
+      } else if (d != 0) {
+        fn(j, d, 0u);
+      }
+    } else if (d != 0) {
+      fn(j, d, 0u);  // multiexp.go:788-800
+    }
+  }
+}
+
+template <class G>
+__global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
+                              uint32_t nb, uint32_t* __restrict__ hist) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    typename G::Fr s = load_vec_ro(scalars + i);
+    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t) { atomicAdd(&hist[(uint32_t)j * nb + mag - 1u], 1u); });
+  }
+}
+
+// entries are filled from the back of each bucket's range: pos = offsets[b] + (old count - 1);
+// the histogram counts down to zero and is clean for the next call.
+template <class G>
+__global__ void k_digits_scatter(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
+                                 uint32_t nb, uint32_t* __restrict__ hist,
+                                 const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    typename G::Fr s = load_vec_ro(scalars + i);
+    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t sign) {
+      uint32_t b = (uint32_t)j * nb + mag - 1u;
+      uint32_t old = atomicSub(&hist[b], 1u);
+      entries[offsets[b] + old - 1u] = (i << 1) | sign;
+    });
+  }
+}
+
+// test hook: digits in the reference's encoding (multiexp.go:779-785), out[w*n + i]
+template <class G>
+__global__ void k_digits_dump(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
+                              uint32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    typename G::Fr s = load_vec_ro(scalars + i);
+    for (int j = 0; j < nwin; j++) out[(size_t)j * n + i] = 0;
+    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t sign) {
+      out[(size_t)j * n + i] = sign ? (((mag - 1u) << 1) | 1u) : (mag << 1);
+    });
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b: exclusive scan over the histogram (nb_total entries) -> offsets[0..nb_total]
+// three-phase: per-block totals, scan of the totals (one block), per-block scan + prefix.
+// ------------------------------------------------------------------------------------------
+
+GMSM_D uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in *total
+GMSM_D uint32_t block_excl_scan(uint32_t v, uint32_t* smem /* >= 33 */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v);
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0;
+    uint32_t wi = warp_incl_scan(w);
+    smem[lane] = wi - w;
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  uint32_t res = smem[warp] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+static __global__ void k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t smem[33];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  uint32_t tot;
+  block_excl_scan(s, smem, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan in place over nblocks values, grand total -> *grand
+static __global__ void k_scan_top(uint32_t* __restrict__ block_sums, uint32_t nblocks, uint32_t* __restrict__ grand) {
+  __shared__ uint32_t smem[33];
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < nblocks) ? block_sums[i] : 0;
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(v, smem, &tot);
+    if (i < nblocks) block_sums[i] = running + ex;
+    running += tot;
+  }
+  if (threadIdx.x == 0) *grand = running;
+}
+
+static __global__ void k_scan_final(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ block_sums,
+                             uint32_t* __restrict__ out) {
+  __shared__ uint32_t smem[33];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan(s, smem, &tot) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// first index in offsets[0..len) with offsets[idx] > key  (offsets non-decreasing)
+GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, uint32_t key) {
+  uint32_t lo = 0, hi = len;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: bucket accumulation as a load-balanced segmented reduction.
+// The bucket-ordered entry list (length M = offsets[nb_total]) is cut into chunks of K entries, one
+// thread per chunk, so the work per thread is constant whatever the digit distribution (the
+// reference needs chunkStat weights and a two-goroutine split for skewed windows, multiexp.go:185-203).
+// A thread keeps the running bucket sum in registers (extended Jacobian, mixed adds with the
+// reference's exact special cases) and flushes it at each bucket boundary:
+//   * bucket begins inside the chunk  -> the thread owns it: buckets[b] = sum (or += in rmw mode)
+//   * bucket began in an earlier chunk -> the partial goes to carries[t] (joined by k_carry_level)
+// ------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
+             const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
+             XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,
+             uint32_t* __restrict__ carry_ids, int rmw) {
+  using F = typename G::F;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const uint32_t M = offsets[nb_total];
+  const uint64_t start64 = (uint64_t)t * K;
+  if (start64 >= M) {
+    carry_ids[t] = ID_NONE;
+    return;
+  }
+  const uint32_t start = (uint32_t)start64;
+  const uint32_t end = (M - start < K) ? M : start + K;
+
+  uint32_t b = upper_bound_u32(offsets, nb_total + 1, start) - 1u;
+  uint32_t bend = offsets[b + 1];
+  bool owner = (offsets[b] == start);
+  uint32_t my_carry = ID_NONE;
+  XYZZ<F> acc = XYZZ<F>::inf();
+
+  uint32_t e = entries[start];
+  Affine<F> pt = load_vec_ro(points + (e >> 1));
+  for (uint32_t pos = start; pos < end; pos++) {
+    // software pipeline: issue the next entry / point loads before the arithmetic of this one
+    uint32_t e_next = 0;
+    Affine<F> pt_next;
+    const bool has_next = (pos + 1 < end);
+    if (has_next) {
+      e_next = entries[pos + 1];
+      pt_next = load_vec_ro(points + (e_next >> 1));
+    }
+    if (pos == bend) {
+      // bucket boundary: flush, move to the bucket that contains `pos`
+      if (owner) {
+        if (rmw) {
+          XYZZ<F> old = load_vec(buckets + b);
+          xyzz_add_cold(old, acc);
+          store_vec(buckets + b, old);
+        } else {
+          store_vec(buckets + b, acc);
+        }
+      } else {
+        store_vec(carries + t, acc);
+        my_carry = b;
+      }
+      b++;
+      if (offsets[b + 1] == pos) b = upper_bound_u32(offsets, nb_total + 1, pos) - 1u;  // skip empty buckets
+      bend = offsets[b + 1];
+      owner = true;
+      acc = XYZZ<F>::inf();
+    }
+    xyzz_add_mixed(acc, pt, (e & 1u) != 0);
+    if (has_next) {
+      e = e_next;
+      pt = pt_next;
+    }
+  }
+  if (owner) {
+    if (rmw) {
+      XYZZ<F> old = load_vec(buckets + b);
+      xyzz_add_cold(old, acc);
+      store_vec(buckets + b, old);
+    } else {
+      store_vec(buckets + b, acc);
+    }
+  } else {
+    store_vec(carries + t, acc);
+    my_carry = b;
+  }
+  carry_ids[t] = my_carry;
+}
+
+// K2b: one level of the carry join.  Input: (id, partial) items ordered by id, ID_NONE = empty slot;
+// the items of one bucket are contiguous.  A thread walks K2 consecutive items, sums runs of equal id;
+// a run that starts in this thread's range is owned (bucket[id] += sum, exclusive within a level);
+// a run continued from the previous range is forwarded to the next level.
+template <class G>
+__global__ void __launch_bounds__(128)
+k_carry_level(const XYZZ<typename G::F>* __restrict__ in_pts, const uint32_t* __restrict__ in_ids, uint32_t n_in,
+              uint32_t K2, XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ out_pts,
+              uint32_t* __restrict__ out_ids) {
+  using F = typename G::F;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_out = (n_in + K2 - 1) / K2;
+  if (t >= n_out) return;
+  const uint32_t start = t * K2;
+  const uint32_t end = (n_in - start < K2) ? n_in : start + K2;
+  uint32_t cur = ID_NONE, out_id = ID_NONE;
+  bool owner = true;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = start; i <= end; i++) {
+    uint32_t id = (i < end) ? in_ids[i] : ID_NONE;
+    if (id == cur && id != ID_NONE) {
+      XYZZ<F> q = load_vec(in_pts + i);
+      xyzz_add_cold(acc, q);
+      continue;
+    }
+    if (cur != ID_NONE) {  // run ended: flush
+      if (owner) {
+        XYZZ<F> old = load_vec(buckets + cur);
+        xyzz_add_cold(old, acc);
+        store_vec(buckets + cur, old);
+      } else {
+        store_vec(out_pts + t, acc);
+        out_id = cur;
+      }
+      cur = ID_NONE;
+    }
+    if (id != ID_NONE) {
+      cur = id;
+      acc = load_vec(in_pts + i);
+      owner = !(i == start && start > 0 && in_ids[start - 1] == id);
+    }
+  }
+  out_ids[t] = out_id;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: bucket reduction.  Window total = sum_k (k+1) * B[k]  (multiexp_jacobian.go:44-52, a serial
+// running sum in the reference).  Parallel form: segment s covers buckets [sL, sL+L):
+//   sum_{k in seg} (k+1) B[k] = tot_s + (sL) * run_s,   run_s = sum B[k], tot_s = local running-sum
+// each thread also applies the small scalar sL by double-and-add, so segments are independent and the
+// window total is a plain sum of the segment results (k_sum_groups).
+// ------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(128)
+k_bucket_segments(const XYZZ<typename G::F>* __restrict__ buckets, int nwin, uint32_t nb, uint32_t nb_last,
+                  uint32_t L, uint32_t S, XYZZ<typename G::F>* __restrict__ seg_out) {
+  using F = typename G::F;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)nwin * S) return;
+  const uint32_t j = gid / S, s = gid % S;
+  const uint32_t nbj = (j == (uint32_t)nwin - 1) ? nb_last : nb;
+  const uint32_t lo = s * L;
+  if (lo >= nbj) {
+    store_vec(seg_out + gid, XYZZ<F>::inf());
+    return;
+  }
+  const uint32_t hi = (nbj - lo < L) ? nbj : lo + L;
+  const XYZZ<F>* base = buckets + (size_t)j * nb;
+  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+  for (uint32_t k = hi; k-- > lo;) {
+    XYZZ<F> bk = load_vec(base + k);
+    xyzz_add_cold(run, bk);
+    xyzz_add_cold(tot, run);
+  }
+  if (lo > 0 && !run.is_inf()) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+      acc = xyzz_double_cold(acc);
+      if ((lo >> bit) & 1u) xyzz_add_cold(acc, run);
+    }
+    xyzz_add_cold(tot, acc);
+  }
+  store_vec(seg_out + gid, tot);
+}
+
+// out[j][g] = sum_{i in [gR, gR+R)} in[j][i]
+template <class G>
+__global__ void __launch_bounds__(128)
+k_sum_groups(const XYZZ<typename G::F>* __restrict__ in, uint32_t in_per_win, uint32_t R, uint32_t out_per_win,
+             int nwin, XYZZ<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (uint32_t)nwin * out_per_win) return;
+  const uint32_t j = gid / out_per_win, g = gid % out_per_win;
+  uint32_t lo = g * R, hi = lo + R;
+  if (hi > in_per_win) hi = in_per_win;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = lo; i < hi; i++) {
+    XYZZ<F> q = load_vec(in + (size_t)j * in_per_win + i);
+    xyzz_add_cold(acc, q);
+  }
+  store_vec(out + (size_t)j * out_per_win + g, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: finalize (one warp).  partials[r][j], r < nranks, j < nwin.
+// ------------------------------------------------------------------------------------------
+template <class G>
+__global__ void k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int nranks, int nwin, int c,
+                           XYZZ<typename G::F>* __restrict__ scratch /* nwin */, Jac<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  // lanes sum over ranks, window-parallel
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+    XYZZ<F> acc = load_vec(partials + j);
+    for (int r = 1; r < nranks; r++) {
+      XYZZ<F> q = load_vec(partials + (size_t)r * nwin + j);
+      xyzz_add_cold(acc, q);
+    }
+    store_vec(scratch + j, acc);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  XYZZ<F> acc = load_vec(scratch + (nwin - 1));
+  for (int j = nwin - 2; j >= 0; j--) {
+    for (int l = 0; l < c; l++) acc = xyzz_double_cold(acc);
+    XYZZ<F> q = load_vec(scratch + j);
+    xyzz_add_cold(acc, q);
+  }
+  Jac<F> jac = xyzz_to_jac(acc);
+  Affine<F> a = jac_to_affine(jac);
+  Jac<F> o;
+  if (jac.z.is_zero()) {
+    o = Jac<F>{F::zero(), F::zero(), F::zero()};
+  } else {
+    o = Jac<F>{a.x, a.y, F::one()};
+  }
+  store_vec(out, o);
+}
+
+// ------------------------------------------------------------------------------------------
+// base generator: out[t*m + i] = [start + t*m + i] * base  (affine), one thread per m consecutive
+// multiples: double-and-add to the first one, mixed adds for the rest, one inversion per thread
+// (Montgomery trick over ZZZ; 1/ZZ = ZZ^2 / ZZZ^2).
+// ------------------------------------------------------------------------------------------
+static constexpr int GEN_M = 16;
+template <class G>
+__global__ void __launch_bounds__(128)
+k_generate_multiples(const Affine<typename G::F>* __restrict__ base_p, uint64_t start, uint64_t n,
+                     Affine<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t first = t * GEN_M;
+  if (first >= n) return;
+  const Affine<F> base = load_vec_ro(base_p);
+  uint64_t k = start + first;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int bit = 63; bit >= 0; bit--) {
+    acc = xyzz_double_cold(acc);
+    if ((k >> bit) & 1ull) xyzz_add_mixed(acc, base, false);
+  }
+  XYZZ<F> pts[GEN_M];
+  F pref[GEN_M];
+  F prod = F::one();
+  const int cnt = (n - first < (uint64_t)GEN_M) ? (int)(n - first) : GEN_M;
+  for (int i = 0; i < cnt; i++) {
+    pts[i] = acc;
+    pref[i] = prod;  // product of ZZZ of points before i (infinity contributes 1)
+    if (!acc.is_inf()) prod = f_mul(prod, acc.zzz);
+    xyzz_add_mixed(acc, base, false);
+  }
+  F inv = f_inv(prod);
+  for (int i = cnt - 1; i >= 0; i--) {
+    Affine<F> a = Affine<F>::inf();
+    if (!pts[i].is_inf()) {
+      F i3 = f_mul(inv, pref[i]);        // 1/ZZZ_i
+      inv = f_mul(inv, pts[i].zzz);
+      F i2 = f_mul(f_sqr(pts[i].zz), f_sqr(i3));  // 1/ZZ_i
+      a.x = f_mul(pts[i].x, i2);
+      a.y = f_mul(pts[i].y, i3);
+    }
+    store_vec(out + first + i, a);
+  }
+}
+
+// test hook kernel (element-wise ops are defined in testops.cuh, shared with the host formula check)
+#if defined(__CUDACC__)
+template <class G>
+__global__ void k_test_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, uint32_t n) {
+  int wa, wb, wo;
+  test_op_sizes<G>(op, &wa, &wb, &wo);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    test_op_one<G>(op, a + (size_t)i * wa, b + (size_t)i * wb, o + (size_t)i * wo);
+}
+#endif
+
+}  // namespace gmsm

@@ -1,0 +1,51 @@
+"""Multi-GPU MultiExp: one process per GPU (torch.distributed, NCCL over NVLink), points/scalars
+sharded contiguously, ONE tiny exchange at the end.
+
+MSM is a sum over independent (P_i, s_i) terms; the reference exploits this with its recursive
+halving joined by one AddAssign (ecc/bn254/multiexp.go:128-140).  Here rank r owns indices
+[r*n/G, (r+1)*n/G), runs the full bucket pass on its slice and produces W per-window partial sums
+(extended Jacobian, 128 B each for bn254 G1).  Elliptic-curve addition is not an NCCL reduction
+operator, so the "allreduce of one partial point per window" is an all-gather of the W partials
+(2 KiB per rank) followed by a local per-window add + Horner (gmsm_ctx_finalize_device) on every rank.
+"""
+from __future__ import annotations
+
+
+def shard_range(n: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of n items for `rank` of `world`"""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d out of range for world size %d" % (rank, world))
+    return n * rank // world, n * (rank + 1) // world
+
+
+def gather_partials(local, world: int, group=None):
+    """all-gather equal-sized 1-D tensors -> concatenation ordered by rank (works for NCCL and gloo)"""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    if dist.get_backend(group) == "gloo":
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        return torch.cat(parts)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
+class ShardedMultiExp:
+    """engine + process group.  msm() returns the Jacobian triple (device tensor) on every rank."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def msm(self, d_points_shard, d_scalars_shard, n_local: int):
+        partials = self.engine.window_sums(d_points_shard, d_scalars_shard, n_local)
+        allp = gather_partials(partials, self.world, self.group)
+        return self.engine.finalize(allp, self.world)

@@ -1,0 +1,140 @@
+/* gmsm.h -- C ABI of the B200-native multi-scalar-multiplication engine.
+ *
+ * Drop-in boundary for ConsenSys/gnark-crypto's MultiExp (all citations relative to the
+ * reference tree):
+ *
+ *   (*G1Jac).MultiExp(points []G1Affine, scalars []fr.Element, config ecc.MultiExpConfig)
+ *       ecc/bn254/multiexp.go:32        ecc/bls12-381/multiexp.go:32
+ *   (*G2Jac).MultiExp                   ecc/bn254/multiexp.go:357       ecc/bls12-381/multiexp.go:355
+ *   (*G1Affine).MultiExp / (*G2Affine).MultiExp  (:20, :345) keep calling the Jac version.
+ *   ecc.MultiExpConfig{NbTasks int}     ecc/ecc.go:107-110
+ *
+ * The reference has no FFI; a cgo shim binds these symbols from a build-tagged
+ * sibling of the generated multiexp.go.  Buffers are passed exactly as Go holds them:
+ *
+ *   points  : n x {X, Y}; each coordinate L little-endian uint64 limbs in Montgomery form
+ *             (L = 4 bn254, 6 bls12-381; G2 coordinates are {A0, A1} pairs); infinity = all zero
+ *             (g1.go:41-47,178-180).  64 / 96 / 128 / 192 bytes per point.
+ *   scalars : n x 4 uint64, Montgomery form, reduced (fr/element.go:36).
+ *   out     : Jacobian {X, Y, Z}, 3 x L (G2: 3 x 2L) uint64, Montgomery form.  The engine writes the
+ *             affine-normalised representative (X, Y, One), or (0, 0, 0) for infinity.  It is
+ *             G1Jac.Equal to what the Go path returns and FromJacobian of it is limb-identical.
+ *   Only 8-byte alignment of host pointers is assumed.  All functions are thread-safe.
+ *
+ * Return value: 0 on success, otherwise a GMSM_E* code; gmsm_last_error() gives the text for the
+ * calling thread (the shim turns it into the Go `error`; the two reference error strings,
+ * multiexp.go:61-71, are reproduced verbatim).
+ */
+#ifndef GMSM_H
+#define GMSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GMSM_BN254_G1 = 0,
+  GMSM_BN254_G2 = 1,
+  GMSM_BLS12381_G1 = 2,
+  GMSM_BLS12381_G2 = 3
+} gmsm_curve_t;
+
+enum {
+  GMSM_OK = 0,
+  GMSM_EINVAL = 1,   /* bad argument (incl. the reference's "invalid config: config.NbTasks > 1024") */
+  GMSM_ECUDA = 2,    /* CUDA runtime error */
+  GMSM_ENOMEM = 3,   /* device allocation failed */
+  GMSM_ENODEV = 4    /* no CUDA device: the engine has NO CPU fallback */
+};
+
+const char* gmsm_last_error(void);
+const char* gmsm_version(void);
+
+/* sizes in bytes for a curve: affine point, scalar, Jacobian output, one extended-Jacobian partial */
+size_t gmsm_affine_bytes(gmsm_curve_t curve);
+size_t gmsm_scalar_bytes(gmsm_curve_t curve);
+size_t gmsm_jac_bytes(gmsm_curve_t curve);
+size_t gmsm_xyzz_bytes(gmsm_curve_t curve);
+
+/* ---- 1. one-shot drop-ins: host buffers in, host Jacobian out (replaces multiexp.go:32 / :357) ----
+ * nb_tasks mirrors config.NbTasks: <= 0 means "default", > 1024 is the reference's error; it does
+ * not otherwise influence the GPU schedule.  */
+int gmsm_bn254_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                           uint64_t out_jac[12]);
+int gmsm_bn254_g2_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                           uint64_t out_jac[24]);
+int gmsm_bls12381_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[18]);
+int gmsm_bls12381_g2_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[36]);
+int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n,
+                  int nb_tasks, uint64_t* out_jac);
+
+/* ---- 2. resident bases (the prover flow: SRS / proving-key points are static, kzg.Commit
+ * ecc/bn254/kzg/kzg.go:159-176 passes pk.G1[:len(p)]) ---- */
+typedef struct gmsm_bases gmsm_bases_t;
+gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size_t n, int device);
+/* MSM over bases[offset, offset+n) with host scalars */
+int gmsm_bases_multiexp(gmsm_bases_t* bases, size_t offset, const uint64_t* scalars, size_t n,
+                        int nb_tasks, uint64_t* out_jac);
+void gmsm_bases_free(gmsm_bases_t* bases);
+
+/* ---- 3. device-level engine (device pointers; what bench.py times with inputs resident in HBM and
+ * what the multi-GPU path composes).  `stream` is a cudaStream_t (NULL = default stream). ---- */
+typedef struct gmsm_ctx gmsm_ctx_t;
+/* c = 0: window width from the cost model; otherwise 2 <= c <= 24 (the reference's c in 2..16 are a
+ * subset: tests sweep them like multiexp_test.go:95-126) */
+gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, int device);
+void gmsm_ctx_destroy(gmsm_ctx_t* ctx);
+int gmsm_ctx_window_bits(const gmsm_ctx_t* ctx);
+int gmsm_ctx_num_windows(const gmsm_ctx_t* ctx);
+size_t gmsm_ctx_workspace_bytes(const gmsm_ctx_t* ctx);
+/* number of kernels launched by the last msm call on this ctx (bench.py's gpu_launches) */
+int gmsm_ctx_last_launches(const gmsm_ctx_t* ctx);
+/* full MSM: d_out_jac receives the Jacobian triple (device memory, gmsm_jac_bytes) */
+int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
+                        void* d_out_jac, void* stream);
+/* per-window partial sums only (W extended-Jacobian points, W * gmsm_xyzz_bytes): the per-rank
+ * result that ranks exchange over NCCL (reference analogue: the halves joined by AddAssign,
+ * multiexp.go:128-140) */
+int gmsm_ctx_window_sums_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
+                                void* d_partials, void* stream);
+/* combine nranks x W gathered partials: per-window sum over ranks, Horner over windows
+ * (msmReduceChunk, multiexp.go:302-315), normalise; d_out_jac as above */
+int gmsm_ctx_finalize_device(gmsm_ctx_t* ctx, const void* d_partials, int nranks, void* d_out_jac,
+                             void* stream);
+/* timings of the last msm call's stages in milliseconds (CUDA events on the call's stream), filled only
+ * when enabled with gmsm_ctx_set_profiling(ctx, 1): [digits+hist, scan, scatter, accumulate,
+ * carries, bucket-reduce, finalize, total] */
+void gmsm_ctx_set_profiling(gmsm_ctx_t* ctx, int on);
+int gmsm_ctx_last_stage_ms(gmsm_ctx_t* ctx, float out_ms[8]);
+
+/* ---- 4. base generation (fixed-base helper): out[i] = [start + i] * base, affine,
+ * device pointers; used to build on-curve benchmark inputs without the Go toolchain ---- */
+int gmsm_generate_multiples_device(gmsm_curve_t curve, const uint64_t* base_affine_host, uint64_t start,
+                                   size_t n, void* d_out_points, void* stream);
+
+/* ---- 5. test hooks: element-wise device functions, used by tests/ to check the sm_100a field and
+ * point arithmetic against the oracle.  a, b, out are HOST arrays of n elements each. ---- */
+enum {
+  GMSM_OP_FMUL = 0, GMSM_OP_FADD = 1, GMSM_OP_FSUB = 2, GMSM_OP_FSQR = 3, GMSM_OP_FNEG = 4,
+  GMSM_OP_FDBL = 5, GMSM_OP_FINV = 6,      /* coordinate field (Fp for G1, Fp2 for G2) */
+  GMSM_OP_ADD_MIXED = 7,                   /* a: xyzz, b: affine -> xyzz */
+  GMSM_OP_SUB_MIXED = 8,
+  GMSM_OP_ADD = 9,                         /* a: xyzz, b: xyzz -> xyzz */
+  GMSM_OP_DOUBLE = 10,                     /* a: xyzz -> xyzz */
+  GMSM_OP_TO_AFFINE = 11,                  /* a: xyzz -> affine */
+  GMSM_OP_FR_FROM_MONT = 12                /* a: scalar -> canonical scalar */
+};
+int gmsm_test_op(gmsm_curve_t curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* out,
+                 size_t n);
+/* digits of partitionScalars (multiexp.go:709-803) as the device computes them: out[w*n + i] */
+int gmsm_test_digits(gmsm_curve_t curve, int c, const uint64_t* scalars, size_t n, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMSM_H */

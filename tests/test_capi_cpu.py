@@ -1,0 +1,72 @@
+"""CPU-side checks of the product boundary: libgmsm.so loads, exports every symbol include/gmsm.h
+declares, reports sizes, and REFUSES to compute without a GPU (no CPU fallback).  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pkg():
+    import gnark_crypto_b200 as pkg
+
+    return pkg
+
+
+def test_header_symbols_exported():
+    pkg = _pkg()
+    L = pkg._native.lib()
+    hdr = open(os.path.join(ROOT, "include", "gmsm.h")).read()
+    declared = set(re.findall(r"\b(gmsm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gmsm_curve_t"}
+    assert declared == set(pkg._native.SYMBOLS), declared ^ set(pkg._native.SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_sizes_match_go_layout():
+    pkg = _pkg()
+    L = pkg._native.lib()
+    # affine 64 / 128 / 96 / 192 B, scalars 32 B, Jacobian 96 / 192 / 144 / 288 B
+    assert [L.gmsm_affine_bytes(c) for c in range(4)] == [64, 128, 96, 192]
+    assert [L.gmsm_scalar_bytes(c) for c in range(4)] == [32] * 4
+    assert [L.gmsm_jac_bytes(c) for c in range(4)] == [96, 192, 144, 288]
+    assert [L.gmsm_xyzz_bytes(c) for c in range(4)] == [128, 256, 192, 384]
+    assert b"sm_100a" in L.gmsm_version()
+
+
+def test_reference_error_strings():
+    pkg = _pkg()
+    pts = np.zeros((3, 8), dtype=np.uint64)
+    sc = np.zeros((2, 4), dtype=np.uint64)
+    with pytest.raises(pkg.MultiExpError, match=r"len\(points\) != len\(scalars\)"):
+        pkg.G1Jac().MultiExp(pts, sc, pkg.MultiExpConfig())
+    with pytest.raises(pkg.MultiExpError, match=r"invalid config: config.NbTasks > 1024"):
+        pkg.G1Jac().MultiExp(pts, np.zeros((3, 4), dtype=np.uint64), pkg.MultiExpConfig(NbTasks=1025))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device refusal is exercised on the CPU-only container")
+    pkg = _pkg()
+    pts = np.zeros((3, 8), dtype=np.uint64)
+    sc = np.ones((3, 4), dtype=np.uint64)
+    with pytest.raises(pkg.MultiExpError, match="no CUDA device|no CPU fallback|CUDA"):
+        pkg.G1Jac().MultiExp(pts, sc, pkg.MultiExpConfig())
+    with pytest.raises(pkg.MultiExpError):
+        pkg.G1Jac().MultiExp(pts[:0], sc[:0], pkg.MultiExpConfig())  # even n = 0 needs the device
+
+
+def test_product_does_not_import_oracle():
+    # the product path must never route through oracle/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gnark-crypto_b200")):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle/|libmsmref", src, re.M), f
