@@ -103,9 +103,10 @@ GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn)
       carry = 0;
       if (d > maxd) {
         // negative digit: d - 2^c; magnitude 2^c - d
+        // (d == 2^c, i.e. an all-ones window plus carry, gives digit 0 with a carry: nothing to add)
         uint32_t mag = (1u << c) - d;
         carry = 1;
-        fn(j, mag, 1u);
+        if (mag != 0) fn(j, mag, 1u);
       } else if (d != 0) {
         fn(j, d, 0u);
       }
