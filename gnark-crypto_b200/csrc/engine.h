@@ -45,6 +45,7 @@ struct gmsm_ctx {
   uint32_t* offsets = nullptr;   // nb_total + 1
   uint32_t* block_sums = nullptr;
   uint32_t* entries = nullptr;   // max_n * W (+pad)
+  uint32_t* digits = nullptr;    // max_n * W, chunk-major (digits[j*n + i])
   void* buckets = nullptr;       // nb_total xyzz
   void* carries[2] = {nullptr, nullptr};
   uint32_t* carry_ids[2] = {nullptr, nullptr};
@@ -73,7 +74,7 @@ static inline uint32_t pick_K(size_t n, int nwin) {
   double total = (double)n * nwin;
   double k = total / (148.0 * 512.0 * 8.0);
   uint32_t K = 4;
-  while (K < 128 && (double)K < k) K <<= 1;
+  while (K < 256 && (double)K < k) K <<= 1;
   return K;
 }
 

@@ -34,7 +34,7 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->hist);
+    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->digits, c->hist);
     launches++;
     LAUNCH_CHECK();
   }
@@ -49,11 +49,14 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
     LAUNCH_CHECK();
   }
   mark(2);
-  // K1c: scatter
+  // K1c: scatter, one launch per window (L2-resident write set)
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_digits_scatter<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->hist, c->offsets, c->entries);
-    launches++;
+    for (int j = 0; j < p.nwin; j++) {
+      k_scatter_window<<<blocks, 256, 0, st>>>(c->digits + (size_t)j * n, n32, c->hist + (size_t)j * p.nb,
+                                               c->offsets + (size_t)j * p.nb, c->entries);
+      launches++;
+    }
     LAUNCH_CHECK();
   }
   mark(3);

@@ -101,6 +101,7 @@ static int ctx_alloc(gmsm_ctx* c) {
   CK(dmalloc(&c->block_sums, ((nbp + SCAN_TILE - 1) / SCAN_TILE + 8) * 4, &acc));
   const size_t ent = c->max_n * (size_t)p.nwin;
   CK(dmalloc(&c->entries, (ent + 16) * 4, &acc));
+  CK(dmalloc(&c->digits, (ent + 16) * 4, &acc));
   CK(dmalloc(&c->buckets, (size_t)p.nb_total * xyzz, &acc));
   // chunks(n) = ceil(n*W / K(n)) <= max(148*512*8 (+slack), ceil(max_n*W/128))  -- see pick_K
   size_t mc = std::max<size_t>(700000, (ent + 127) / 128 + 1);
@@ -124,7 +125,7 @@ static int ctx_alloc(gmsm_ctx* c) {
 
 static void ctx_free(gmsm_ctx* c) {
   cudaSetDevice(c->device);
-  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->buckets);
+  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->buckets);
   for (int i = 0; i < 2; i++) { cudaFree(c->carries[i]); cudaFree(c->carry_ids[i]); cudaFree(c->seg[i]); }
   cudaFree(c->win_partials); cudaFree(c->fin_scratch);
   for (int i = 0; i < 9; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -140,6 +141,8 @@ extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, 
   if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { set_err(GMSM_ECUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
   if (max_n == 0) max_n = 1;
+  // point gathers are 64-byte random reads: do not let L2 promote them to 128-byte fetches
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   gmsm_ctx* ctx = new gmsm_ctx();
   ctx->curve = curve;
   ctx->device = device;

@@ -85,7 +85,10 @@ template <class G, class Fn>
 GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn) {
   using Fr = typename G::Fr;
   constexpr int N = Fr::N;
-  if (s_mont.is_zero()) return;           // IsZero() on the Montgomery limbs, multiexp.go:743
+  if (s_mont.is_zero()) {                 // IsZero() on the Montgomery limbs, multiexp.go:743
+    for (int j = 0; j < nwin; j++) fn(j, 0u);
+    return;
+  }
   Fr k = fp_from_mont(s_mont);            // Bits(), fr/element.go:855-859
   uint32_t v[N];
 #pragma unroll
@@ -95,49 +98,57 @@ GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn)
   uint32_t carry = 0;
   for (int j = 0; j < nwin; j++) {
     uint32_t d = (v[0] & mask) + carry;
-    // 256-bit (384-bit) logical shift right by c (c < 32)
+    // 256-bit logical shift right by c (c < 32)
 #pragma unroll
     for (int i = 0; i < N - 1; i++) v[i] = __funnelshift_r(v[i], v[i + 1], c);
     v[N - 1] >>= c;
+    uint32_t code;
     if (j < nwin - 1) {
       carry = 0;
       if (d > maxd) {
-        // negative digit: d - 2^c; magnitude 2^c - d
-        // (d == 2^c, i.e. an all-ones window plus carry, gives digit 0 with a carry: nothing to add)
+        // negative digit d - 2^c, magnitude 2^c - d  (0 when an all-ones window meets a carry:
+        // digit 0 with a carry out, nothing to add)
         uint32_t mag = (1u << c) - d;
         carry = 1;
-        if (mag != 0) fn(j, mag, 1u);
-      } else if (d != 0) {
-        fn(j, d, 0u);
+        code = mag ? (((mag - 1u) << 1) | 1u) : 0u;
+      } else {
+        code = d << 1;
       }
-    } else if (d != 0) {
-      fn(j, d, 0u);  // multiexp.go:788-800
+    } else {
+      code = d << 1;  // multiexp.go:788-800: the last window never borrows
     }
+    fn(j, code);
   }
 }
 
+// bucket index inside its window for a non-zero code: magnitude - 1
+GMSM_D uint32_t code_bucket(uint32_t code) { return (code >> 1) - 1u + (code & 1u); }
+
+// K1: digits (stored chunk-major, digits[j*n + i], the reference's layout multiexp.go:785) + histogram
 template <class G>
 __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
-                              uint32_t nb, uint32_t* __restrict__ hist) {
+                              uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     typename G::Fr s = load_vec_ro(scalars + i);
-    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t) { atomicAdd(&hist[(uint32_t)j * nb + mag - 1u], 1u); });
+    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t code) {
+      digits[(size_t)j * n + i] = code;
+      if (code) atomicAdd(&hist[(uint32_t)j * nb + code_bucket(code)], 1u);
+    });
   }
 }
 
-// entries are filled from the back of each bucket's range: pos = offsets[b] + (old count - 1);
-// the histogram counts down to zero and is clean for the next call.
-template <class G>
-__global__ void k_digits_scatter(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
-                                 uint32_t nb, uint32_t* __restrict__ hist,
-                                 const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+// K1c: scatter of ONE window.  Launched window by window so that the randomly written slice of
+// `entries` (<= 4n bytes) and the window's counters stay L2-resident (126 MB) and reach HBM once, as
+// full lines, instead of one read-modify-write per 4-byte store.  Entries of a bucket are filled from
+// the back: pos = offsets[b] + (old count - 1); the histogram counts down to zero.
+static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t* __restrict__ hist_w,
+                                 const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    typename G::Fr s = load_vec_ro(scalars + i);
-    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t sign) {
-      uint32_t b = (uint32_t)j * nb + mag - 1u;
-      uint32_t old = atomicSub(&hist[b], 1u);
-      entries[offsets[b] + old - 1u] = (i << 1) | sign;
-    });
+    uint32_t code = __ldg(digits_w + i);
+    if (code == 0) continue;
+    uint32_t b = code_bucket(code);
+    uint32_t old = atomicSub(&hist_w[b], 1u);
+    entries[offsets_w[b] + old - 1u] = (i << 1) | (code & 1u);
   }
 }
 
@@ -147,10 +158,7 @@ __global__ void k_digits_dump(const typename G::Fr* __restrict__ scalars, uint32
                               uint32_t* __restrict__ out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     typename G::Fr s = load_vec_ro(scalars + i);
-    for (int j = 0; j < nwin; j++) out[(size_t)j * n + i] = 0;
-    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t mag, uint32_t sign) {
-      out[(size_t)j * n + i] = sign ? (((mag - 1u) << 1) | 1u) : (mag << 1);
-    });
+    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t code) { out[(size_t)j * n + i] = code; });
   }
 }
 
@@ -255,7 +263,7 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 //   * bucket began in an earlier chunk -> the partial goes to carries[t] (joined by k_carry_level)
 // ------------------------------------------------------------------------------------------
 template <class G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : 1)
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
              XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,

@@ -1,0 +1,71 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 `gloo` process group.  Checks the shard
+partition and that the all-gather of per-rank window partials is ordered by rank (what
+gmsm_ctx_finalize_device expects: partials[r][j]).  The CUDA composition itself is covered on one GPU by
+tests/test_gpu_msm.py::test_window_sums_and_finalize_compose and on N GPUs by tests/test_gpu_dist.py."""
+import importlib
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    distmod = importlib.import_module("gnark-crypto_b200.dist")
+    W, words = 16, 16  # 16 windows x 128-byte partials (bn254 G1)
+    local = torch.full((W * words,), rank + 1, dtype=torch.int64)
+    local[0] = 1000 + rank
+    allp = distmod.gather_partials(local, world)
+    lo, hi = distmod.shard_range(1000003, rank, world)
+    q.put((rank, allp.tolist(), lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_partials_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 16 * 16
+    for rank, allp, lo, hi in res:
+        assert len(allp) == world * n
+        for r in range(world):
+            assert allp[r * n] == 1000 + r and allp[r * n + 1] == r + 1  # rank-major order
+    assert res[0][2:] == (0, 500001) and res[1][2:] == (500001, 1000003)
+
+
+def test_shard_range_partitions():
+    distmod = importlib.import_module("gnark-crypto_b200.dist")
+    for n in (0, 1, 7, 1 << 24, (1 << 26) + 5):
+        for world in (1, 2, 4, 8):
+            cuts = [distmod.shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
+    with pytest.raises(ValueError):
+        distmod.shard_range(10, 2, 2)
