@@ -313,7 +313,7 @@ def main():
                 return outj
         else:
             dp2 = torch.empty_like(d_points)
-            ds2 = torch.empty_like(d_scalars)
+            ds2 = torch.empty(n * 4, dtype=torch.int64, device=d_points.device)
 
             def e2e_step():
                 dp2.copy_(h_points, non_blocking=True)
@@ -338,7 +338,7 @@ def main():
                        "path": "gmsm_multiexp one-shot (points+scalars H2D every call)" if world == 1 else
                                "pinned host shards -> H2D -> sharded MultiExp -> D2H"}
         if world == 1:
-            launches_e2e = eng.last_launches
+            launches_e2e = native.lib().gmsm_last_oneshot_launches()
             line["gpu_launches"] += launches_e2e * args.steps
             # resident bases (prover flow: SRS static, scalars per call)
             rb = mx.ResidentBases(g, hp.reshape(n, wds), device=local_rank)

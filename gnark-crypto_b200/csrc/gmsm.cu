@@ -21,6 +21,7 @@ using namespace gmsm;
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static int g_last_oneshot_launches = 0;
 
 int gmsm::set_err(int code, const char* fmt, ...) {
   char buf[512];
@@ -33,6 +34,7 @@ int gmsm::set_err(int code, const char* fmt, ...) {
 }
 
 extern "C" const char* gmsm_last_error(void) { return g_err.c_str(); }
+extern "C" int gmsm_last_oneshot_launches(void) { return g_last_oneshot_launches; }
 extern "C" const char* gmsm_version(void) { return "gmsm-b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------
@@ -352,19 +354,79 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   }
   int device = 0;
   if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
-  // per-(curve, device) session: device buffers and the engine context are kept between calls
-  // (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
-  static std::mutex sess_mu;
-  static std::map<std::pair<int, int>, gmsm_bases*> sessions;
-  std::lock_guard<std::mutex> lk(sess_mu);
-  gmsm_bases*& sb = sessions[std::make_pair((int)curve, device)];
-  if (sb && (sb->cap < n || sb->cap > 4 * n + 1024)) { gmsm_bases_free(sb); sb = nullptr; }
-  if (!sb) {
-    sb = bases_alloc(curve, n, device);
-    if (!sb) return g_err.find("no CUDA device") != std::string::npos ? GMSM_ENODEV : GMSM_ECUDA;
+  {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(GMSM_EINVAL, "device %d out of range", device);
   }
-  if (int rc = bases_fill(sb, points, n)) return rc;
-  return gmsm_bases_multiexp(sb, 0, scalars, n, nb_tasks, out_jac);
+  // Per-(curve, device) session: device buffers, streams and the engine context are kept between
+  // calls (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc.
+  // The call is pipelined: the inputs are cut into S contiguous chunks; chunk k+1 crosses PCIe on the
+  // copy stream while chunk k runs K1..K3 on the compute stream (each chunk is an independent
+  // sub-MSM producing W window partials -- the same decomposition as the multi-GPU path and as the
+  // reference's recursive halving, multiexp.go:128-140); one finalize joins the S x W partials.
+  struct Session {
+    size_t cap = 0, chunk_cap = 0;
+    int nchunks_cap = 0;
+    void *d_points = nullptr, *d_scalars = nullptr, *d_partials = nullptr, *d_out = nullptr;
+    gmsm_ctx* ctx = nullptr;
+    cudaStream_t copy_st = nullptr, comp_st = nullptr;
+    cudaEvent_t ev[16] = {};
+  };
+  static std::mutex sess_mu;
+  static std::map<std::pair<int, int>, Session> sessions;
+  std::lock_guard<std::mutex> lk(sess_mu);
+  CK(cudaSetDevice(device));
+  Session& S = sessions[std::make_pair((int)curve, device)];
+  const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
+  int nch = (n >= (1u << 21)) ? 4 : 1;
+  if (const char* e = getenv("GMSM_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) nch = v; }
+  if ((size_t)nch > n) nch = 1;
+  const size_t nc = (n + nch - 1) / nch;
+  if (!S.copy_st) {
+    CK(cudaStreamCreateWithFlags(&S.copy_st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&S.comp_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming));
+    CK(cudaMalloc(&S.d_out, 512));
+  }
+  if (S.cap < n || S.cap > 4 * n + 1024) {
+    cudaFree(S.d_points); cudaFree(S.d_scalars); S.d_points = S.d_scalars = nullptr; S.cap = 0;
+    CK(cudaMalloc(&S.d_points, n * ab));
+    CK(cudaMalloc(&S.d_scalars, n * 32));
+    S.cap = n;
+  }
+  if (!S.ctx || S.ctx->max_n < nc || S.ctx->max_n > 4 * nc + 1024 || S.nchunks_cap < nch) {
+    if (S.ctx) { gmsm_ctx_destroy(S.ctx); S.ctx = nullptr; }
+    cudaFree(S.d_partials); S.d_partials = nullptr;
+    S.ctx = gmsm_ctx_create(curve, nc, 0, device);
+    if (!S.ctx) return GMSM_ECUDA;
+    CK(cudaMalloc(&S.d_partials, (size_t)nch * S.ctx->plan.nwin * xb));
+    S.nchunks_cap = nch;
+  }
+  const GroupVTable* vt = vtable(curve);
+  const char* hp = reinterpret_cast<const char*>(points);
+  const char* hs = reinterpret_cast<const char*>(scalars);
+  int launches = 0;
+  for (int k = 0; k < nch; k++) {
+    const size_t off = (size_t)k * nc;
+    const size_t m = std::min(nc, n - off);
+    CK(cudaMemcpyAsync((char*)S.d_scalars + off * 32, hs + off * 32, m * 32, cudaMemcpyHostToDevice, S.copy_st));
+    CK(cudaMemcpyAsync((char*)S.d_points + off * ab, hp + off * ab, m * ab, cudaMemcpyHostToDevice, S.copy_st));
+    CK(cudaEventRecord(S.ev[k], S.copy_st));
+    CK(cudaStreamWaitEvent(S.comp_st, S.ev[k], 0));
+    std::lock_guard<std::mutex> lk2(S.ctx->mu);
+    if (int rc = vt->window_sums(S.ctx, (char*)S.d_points + off * ab, (char*)S.d_scalars + off * 32, m,
+                                 (char*)S.d_partials + (size_t)k * S.ctx->plan.nwin * xb, S.comp_st)) return rc;
+    launches += S.ctx->last_launches;
+  }
+  if (int rc = vt->finalize(S.ctx, S.d_partials, nch, S.d_out, S.comp_st)) return rc;
+  S.ctx->last_launches = launches + 1;
+  CK(cudaMemcpyAsync(out_jac, S.d_out, jb, cudaMemcpyDeviceToHost, S.comp_st));
+  CK(cudaStreamSynchronize(S.comp_st));
+  CK(cudaStreamSynchronize(S.copy_st));
+  g_last_oneshot_launches = S.ctx->last_launches;
+  return GMSM_OK;
 }
 
 extern "C" int gmsm_bn254_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_BN254_G1, p, s, n, t, out); }

@@ -72,6 +72,8 @@ int gmsm_bls12381_g2_multiexp(const uint64_t* points, const uint64_t* scalars, s
                               uint64_t out_jac[36]);
 int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n,
                   int nb_tasks, uint64_t* out_jac);
+/* kernels launched by the last one-shot call in this process (bench.py's gpu_launches) */
+int gmsm_last_oneshot_launches(void);
 
 /* ---- 2. resident bases (the prover flow: SRS / proving-key points are static, kzg.Commit
  * ecc/bn254/kzg/kzg.go:159-176 passes pk.G1[:len(p)]) ---- */
