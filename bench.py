@@ -193,6 +193,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module("gnark_crypto_b200")
     distmod = importlib.import_module("gnark-crypto_b200.dist")
