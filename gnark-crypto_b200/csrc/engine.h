@@ -50,6 +50,18 @@ struct gmsm_ctx {
   void* carries[2] = {nullptr, nullptr};
   uint32_t* carry_ids[2] = {nullptr, nullptr};
   void* seg[2] = {nullptr, nullptr};
+  // batch-affine accumulation (affine_kernels.cuh); enabled per context (GMSM_AFFINE, default on)
+  bool affine = false;
+  void* aff_buf[2] = {nullptr, nullptr};   // level outputs, ping-pong (affine points)
+  void* aff_pref = nullptr;                // running products before each denominator
+  void* aff_totals = nullptr;              // per-thread total products
+  void* aff_ps = nullptr;                  // per-thread prefix*suffix products inside a scan tile
+  void* aff_bp = nullptr;                  // per-tile products, their exclusive prefixes, their inverses (3 arrays)
+  uint32_t* aff_off[2] = {nullptr, nullptr};
+  uint32_t* aff_counts = nullptr;
+  uint32_t* aff_maxlen = nullptr;          // device
+  uint32_t* aff_maxlen_host = nullptr;     // pinned
+  size_t aff_cap1 = 0, aff_cap2 = 0, aff_tcap = 0;
   void* win_partials = nullptr;  // W xyzz (own result for single-rank msm)
   void* fin_scratch = nullptr;   // W xyzz
   size_t max_chunks = 0;

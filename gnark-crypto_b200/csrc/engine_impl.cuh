@@ -2,6 +2,7 @@
 #pragma once
 #include "engine.h"
 #include "kernels.cuh"
+#include "affine_kernels.cuh"
 
 namespace gmsm {
 
@@ -40,14 +41,16 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
   }
   mark(1);
   // K1b: scan
-  {
+  auto scan_u32 = [&](const uint32_t* in, uint32_t* out) -> int {
     unsigned nb_blocks = nblk(nbp, SCAN_TILE);
-    k_scan_block_sums<<<nb_blocks, SCAN_THREADS, 0, st>>>(c->hist, (uint32_t)nbp, c->block_sums);
+    k_scan_block_sums<<<nb_blocks, SCAN_THREADS, 0, st>>>(in, (uint32_t)nbp, c->block_sums);
     k_scan_top<<<1, 1024, 0, st>>>(c->block_sums, nb_blocks, c->block_sums + nb_blocks);
-    k_scan_final<<<nb_blocks, SCAN_THREADS, 0, st>>>(c->hist, (uint32_t)nbp, c->block_sums, c->offsets);
+    k_scan_final<<<nb_blocks, SCAN_THREADS, 0, st>>>(in, (uint32_t)nbp, c->block_sums, out);
     launches += 3;
     LAUNCH_CHECK();
-  }
+    return GMSM_OK;
+  };
+  if (int rc = scan_u32(c->hist, c->offsets)) return rc;
   mark(2);
   // K1c: scatter, one launch per window (L2-resident write set)
   {
@@ -60,31 +63,94 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
     LAUNCH_CHECK();
   }
   mark(3);
-  // K2: accumulate
-  const uint32_t K = pick_K(n, p.nwin);
-  const size_t nchunks = (n * (size_t)p.nwin + K - 1) / K;
-  if (nchunks > c->max_chunks) return set_err(GMSM_EINVAL, "internal: chunk bound exceeded (%zu > %zu)", nchunks, c->max_chunks);
-  CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
-  {
-    k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
-                                                        buckets, reinterpret_cast<X*>(c->carries[0]), c->carry_ids[0], 0);
+  if (c->affine) {
+    // K2 (batch-affine): balanced tree over the bucket-ordered entries, one shared inversion per level
+    using A = Affine<F>;
+    const uint32_t nbt = p.nb_total;
+    CK(cudaMemsetAsync(c->aff_maxlen, 0, 4, st));
+    k_aff_max_len<<<148 * 4, 256, 0, st>>>(c->offsets, nbt, c->aff_maxlen);
     launches++;
     LAUNCH_CHECK();
-  }
-  mark(4);
-  // K2b: carry join levels
-  {
-    size_t n_in = nchunks;
-    int cur = 0;
-    while (n_in > 1) {
-      size_t n_out = (n_in + c->K2 - 1) / c->K2;
-      k_carry_level<G><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
-                                                        (uint32_t)n_in, c->K2, buckets,
-                                                        reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
+    CK(cudaMemcpyAsync(c->aff_maxlen_host, c->aff_maxlen, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t maxlen = *c->aff_maxlen_host;
+    int nlevels = 0;
+    while (((uint64_t)1 << nlevels) < maxlen) nlevels++;
+    const uint32_t* off_cur = c->offsets;
+    const A* src_cur = nullptr;
+    size_t m_up = n * (size_t)p.nwin;
+    const size_t fe = sizeof(F);
+    F* bp = reinterpret_cast<F*>(c->aff_bp);
+    const size_t bp_stride = c->aff_tcap / 1024 + 8;
+    for (int l = 0; l < nlevels; l++) {
+      uint32_t* off_next = c->aff_off[l & 1];
+      k_aff_level_counts<<<std::min<unsigned>(nblk(nbp, 256), 148u * 8u), 256, 0, st>>>(c->offsets, nbt, l + 1, c->aff_counts);
+      launches++;
+      if (int rc = scan_u32(c->aff_counts, off_next)) return rc;
+      // sum_b ceil(len_b/2) <= (m + #nonempty)/2 and #nonempty <= min(nb, m): non-increasing bound
+      const size_t m_next = std::min(m_up, (m_up + std::min<size_t>(nbt, m_up)) / 2 + 1);
+      uint32_t B = 8;
+      while (B < 128 && (double)B < (double)m_next / (148.0 * 512.0 * 4.0)) B <<= 1;
+      // warp-interleaved slots: a warp owns 32*B consecutive slots; T = threads = thread totals
+      const size_t T = ((m_next + 32 * (size_t)B - 1) / (32 * (size_t)B)) * 32;
+      if (T > c->aff_tcap || m_next > ((l & 1) ? c->aff_cap2 : c->aff_cap1))
+        return set_err(GMSM_EINVAL, "internal: affine level bound exceeded (level %d, T=%zu, m=%zu)", l, T, m_next);
+      A* dst = reinterpret_cast<A*>(c->aff_buf[l & 1]);
+      F* pref = reinterpret_cast<F*>(c->aff_pref);
+      F* totals = reinterpret_cast<F*>(c->aff_totals);
+      F* ps = reinterpret_cast<F*>(c->aff_ps);
+      const unsigned NB = nblk(T, PSCAN_TILE);
+      if (l == 0)
+        k_aff_forward<G, true><<<nblk(T, 128), 128, 0, st>>>(points, c->entries, src_cur, off_cur, off_next, nbt, B, (uint32_t)T, pref, totals);
+      else
+        k_aff_forward<G, false><<<nblk(T, 128), 128, 0, st>>>(points, c->entries, src_cur, off_cur, off_next, nbt, B, (uint32_t)T, pref, totals);
+      k_aff_scan_tiles<G><<<NB, PSCAN_THREADS, 0, st>>>(totals, (uint32_t)T, ps, bp);
+      k_aff_scan_top<G><<<1, PSCAN_THREADS, 0, st>>>(bp, NB, bp + bp_stride, bp + 2 * bp_stride);
+      if (l == 0)
+        k_aff_backward<G, true><<<nblk(T, 128), 128, 0, st>>>(points, c->entries, src_cur, off_cur, off_next, nbt, B, (uint32_t)T, pref, ps, bp + 2 * bp_stride, dst);
+      else
+        k_aff_backward<G, false><<<nblk(T, 128), 128, 0, st>>>(points, c->entries, src_cur, off_cur, off_next, nbt, B, (uint32_t)T, pref, ps, bp + 2 * bp_stride, dst);
+      launches += 4;
+      LAUNCH_CHECK();
+      src_cur = dst;
+      off_cur = off_next;
+      m_up = m_next;
+      (void)fe;
+    }
+    if (nlevels == 0)
+      k_aff_to_buckets<G, true><<<std::min<unsigned>(nblk(nbt, 256), 148u * 8u), 256, 0, st>>>(points, c->entries, src_cur, off_cur, nbt, buckets);
+    else
+      k_aff_to_buckets<G, false><<<std::min<unsigned>(nblk(nbt, 256), 148u * 8u), 256, 0, st>>>(points, c->entries, src_cur, off_cur, nbt, buckets);
+    launches++;
+    LAUNCH_CHECK();
+    mark(4);
+  } else {
+  // K2: accumulate
+    const uint32_t K = pick_K(n, p.nwin);
+    const size_t nchunks = (n * (size_t)p.nwin + K - 1) / K;
+    if (nchunks > c->max_chunks) return set_err(GMSM_EINVAL, "internal: chunk bound exceeded (%zu > %zu)", nchunks, c->max_chunks);
+    CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
+    {
+      k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
+                                                          buckets, reinterpret_cast<X*>(c->carries[0]), c->carry_ids[0], 0);
       launches++;
       LAUNCH_CHECK();
-      n_in = n_out;
-      cur ^= 1;
+    }
+    mark(4);
+    // K2b: carry join levels
+    {
+      size_t n_in = nchunks;
+      int cur = 0;
+      while (n_in > 1) {
+        size_t n_out = (n_in + c->K2 - 1) / c->K2;
+        k_carry_level<G><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
+                                                          (uint32_t)n_in, c->K2, buckets,
+                                                          reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
+        launches++;
+        LAUNCH_CHECK();
+        n_in = n_out;
+        cur ^= 1;
+      }
     }
   }
   mark(5);

@@ -118,6 +118,23 @@ static int ctx_alloc(gmsm_ctx* c) {
   c->seg_S = (nbmax + c->seg_L - 1) / c->seg_L;
   CK(dmalloc(&c->seg[0], (size_t)p.nwin * c->seg_S * xyzz, &acc));
   CK(dmalloc(&c->seg[1], (size_t)p.nwin * ((c->seg_S + 15) / 16) * xyzz, &acc));
+  if (c->affine) {
+    const size_t aff = 8u * c->ci.coord_words, fe = 4u * c->ci.coord_words;
+    const size_t m1 = (ent + std::min(nbp, ent)) / 2 + 2, m2 = (m1 + std::min(nbp, m1)) / 2 + 2;
+    c->aff_cap1 = m1; c->aff_cap2 = m2;
+    c->aff_tcap = std::max<size_t>(700000, m1 / 128 + 2);
+    CK(dmalloc(&c->aff_buf[0], m1 * aff, &acc));
+    CK(dmalloc(&c->aff_buf[1], m2 * aff, &acc));
+    CK(dmalloc(&c->aff_pref, m1 * fe, &acc));
+    CK(dmalloc(&c->aff_totals, c->aff_tcap * fe, &acc));
+    CK(dmalloc(&c->aff_ps, c->aff_tcap * fe, &acc));
+    CK(dmalloc(&c->aff_bp, 3 * (c->aff_tcap / 1024 + 8) * fe, &acc));
+    CK(dmalloc(&c->aff_off[0], (nbp + 8) * 4, &acc));
+    CK(dmalloc(&c->aff_off[1], (nbp + 8) * 4, &acc));
+    CK(dmalloc(&c->aff_counts, (nbp + 8) * 4, &acc));
+    CK(dmalloc(&c->aff_maxlen, 16, &acc));
+    CK(cudaMallocHost((void**)&c->aff_maxlen_host, 16));
+  }
   CK(dmalloc(&c->win_partials, (size_t)p.nwin * xyzz, &acc));
   CK(dmalloc(&c->fin_scratch, (size_t)p.nwin * xyzz, &acc));
   c->ws_bytes = acc;
@@ -130,6 +147,10 @@ static void ctx_free(gmsm_ctx* c) {
   cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->buckets);
   for (int i = 0; i < 2; i++) { cudaFree(c->carries[i]); cudaFree(c->carry_ids[i]); cudaFree(c->seg[i]); }
   cudaFree(c->win_partials); cudaFree(c->fin_scratch);
+  for (int i = 0; i < 2; i++) { cudaFree(c->aff_buf[i]); cudaFree(c->aff_off[i]); }
+  cudaFree(c->aff_pref); cudaFree(c->aff_totals); cudaFree(c->aff_ps); cudaFree(c->aff_bp); cudaFree(c->aff_counts);
+  cudaFree(c->aff_maxlen);
+  if (c->aff_maxlen_host) cudaFreeHost(c->aff_maxlen_host);
   for (int i = 0; i < 9; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 }
 
@@ -151,6 +172,8 @@ extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, 
   ctx->max_n = max_n;
   ctx->ci = ci;
   if (c == 0) c = choose_c(ci.fr_bits, max_n);
+  ctx->affine = true;  // batch-affine bucket accumulation; GMSM_AFFINE=0 selects the extended-Jacobian pass
+  if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
   ctx->plan = make_plan(ci.fr_bits, c);
   if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
     set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 32-bit entry index; shard the MSM", max_n, ctx->plan.nwin);

@@ -18,6 +18,14 @@ def _pkg():
     return pkg
 
 
+@pytest.fixture(params=["affine", "xyzz"])
+def accumulate_mode(request, monkeypatch):
+    """both bucket-accumulation paths: batch-affine tree (default; multiexp_affine.go's counterpart) and
+    the extended-Jacobian segmented reduction (multiexp_jacobian.go's counterpart)"""
+    monkeypatch.setenv("GMSM_AFFINE", "1" if request.param == "affine" else "0")
+    return request.param
+
+
 def _engine_msm(g, pts, s, c):
     pkg = _pkg()
     n = pts.shape[0]
@@ -31,7 +39,7 @@ def _engine_msm(g, pts, s, c):
 
 
 @pytest.mark.parametrize("g,n", [("bn254_g1", 2000), ("bls12381_g1", 1200), ("bn254_g2", 1000), ("bls12381_g2", 500)])
-def test_all_window_sizes_agree_with_oracle(g, n):
+def test_all_window_sizes_agree_with_oracle(g, n, accumulate_mode):
     """every c the reference implements (2..16) plus the wider windows the GPU model may pick"""
     pts, s = make_inputs(g, n, 1234)
     want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
@@ -47,7 +55,7 @@ def test_all_window_sizes_agree_with_oracle(g, n):
         assert np.array_equal(jac_to_affine_bytes(g, jac), want), c
 
 
-def test_config1_n65536_bn254_g1():
+def test_config1_n65536_bn254_g1(accumulate_mode):
     """BASELINE.json configs[0]: bn254 G1, n = 2^16, random scalars; oracle = the reference algorithm
     single-threaded with the reference's own window choice (c = 13)."""
     g = "bn254_g1"
@@ -73,7 +81,7 @@ def test_config1_n65536_bn254_g1():
 
 
 @pytest.mark.parametrize("g", ["bn254_g1", "bn254_g2", "bls12381_g1"])
-def test_infinity_zero_and_empty(g):
+def test_infinity_zero_and_empty(g, accumulate_mode):
     pkg = _pkg()
     A1, J1, A2, J2 = pkg.curve_package(g.split("_")[0])
     Jac = J1 if g.endswith("g1") else J2
@@ -105,7 +113,7 @@ def test_closed_form_sum_of_squares():
 
 
 @pytest.mark.parametrize("kind", ["smallvalues", "redundancy", "one_bucket", "all_equal_points"])
-def test_skewed_scalar_distributions(kind):
+def test_skewed_scalar_distributions(kind, accumulate_mode):
     """the reference's benchmark distributions (multiexp_test.go:319-334) and harder skews: the
     chunked segmented reduction + carry levels must stay correct when buckets span many chunks"""
     g = "bn254_g1"
@@ -128,7 +136,7 @@ def test_skewed_scalar_distributions(kind):
 
 
 @pytest.mark.parametrize("g,n", [("bn254_g1", 1 << 20), ("bls12381_g1", 1 << 18), ("bn254_g2", 1 << 17)])
-def test_large_closed_form_on_device_bases(g, n):
+def test_large_closed_form_on_device_bases(g, n, accumulate_mode):
     """size-independent property at large n: bases [i+1]B generated on the device, result must equal
     [sum (i+1) s_i mod r] B (the KZG TestCommit identity, kzg_test.go:209-239); also pins the device
     base generator against the oracle on a sample."""
@@ -152,7 +160,7 @@ def test_large_closed_form_on_device_bases(g, n):
         eng.close()
 
 
-def test_window_sums_and_finalize_compose():
+def test_window_sums_and_finalize_compose(accumulate_mode):
     """the multi-GPU decomposition on one device: split the inputs in 3 shards, per-shard window
     partials, finalize over the 3 'ranks' == MSM of the whole"""
     import torch
