@@ -10,6 +10,7 @@ Layout:
 """
 from . import _native  # noqa: F401
 from .multiexp import (  # noqa: F401
+    BatchScalarMultiplication,
     CURVES,
     Engine,
     G1Affine,
@@ -21,4 +22,4 @@ from .multiexp import (  # noqa: F401
     curve_package,
 )
 
-__all__ = ["CURVES", "Engine", "G1Affine", "G1Jac", "G2Affine", "G2Jac", "MultiExpConfig", "MultiExpError", "curve_package"]
+__all__ = ["BatchScalarMultiplication", "CURVES", "Engine", "G1Affine", "G1Jac", "G2Affine", "G2Jac", "MultiExpConfig", "MultiExpError", "curve_package"]

@@ -8,7 +8,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgmsm.so")
+# GMSM_LIB=<tag> selects an experimental build variant (see build.py); default is libgmsm.so
+_TAG = os.environ.get("GMSM_LIB", "")
+LIB_PATH = os.path.join(HERE, "libgmsm%s.so" % ("_" + _TAG if _TAG else ""))
 
 GMSM_OK, GMSM_EINVAL, GMSM_ECUDA, GMSM_ENOMEM, GMSM_ENODEV = 0, 1, 2, 3, 4
 
@@ -19,7 +21,7 @@ SYMBOLS = [
     "gmsm_multiexp", "gmsm_last_oneshot_launches", "gmsm_bases_upload", "gmsm_bases_multiexp", "gmsm_bases_free",
     "gmsm_ctx_create", "gmsm_ctx_destroy", "gmsm_ctx_window_bits", "gmsm_ctx_num_windows", "gmsm_ctx_workspace_bytes",
     "gmsm_ctx_last_launches", "gmsm_ctx_msm_device", "gmsm_ctx_window_sums_device", "gmsm_ctx_finalize_device",
-    "gmsm_ctx_set_profiling", "gmsm_ctx_last_stage_ms", "gmsm_generate_multiples_device", "gmsm_test_op", "gmsm_test_digits",
+    "gmsm_ctx_set_profiling", "gmsm_ctx_last_stage_ms", "gmsm_generate_multiples_device", "gmsm_batch_scalar_mul", "gmsm_test_op", "gmsm_test_digits",
 ]
 
 _lib = None
@@ -68,6 +70,7 @@ def lib() -> ctypes.CDLL:
     L.gmsm_ctx_set_profiling.restype = None
     L.gmsm_ctx_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.gmsm_generate_multiples_device.argtypes = [i32, vp, ctypes.c_uint64, sz, vp, vp]
+    L.gmsm_batch_scalar_mul.argtypes = [i32, vp, vp, sz, vp]
     L.gmsm_test_op.argtypes = [i32, i32, vp, vp, vp, sz]
     L.gmsm_test_digits.argtypes = [i32, i32, vp, sz, vp]
     _lib = L

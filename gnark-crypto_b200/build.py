@@ -10,8 +10,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libgmsm.so")
+# GMSM_BUILD_TAG=<tag> builds an experimental variant into build_<tag>/ and libgmsm_<tag>.so (loaded with
+# GMSM_LIB=<tag>); extra nvcc flags for it come from GMSM_NVCC_EXTRA
+TAG = os.environ.get("GMSM_BUILD_TAG", "")
+BUILD = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libgmsm%s.so" % ("_" + TAG if TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -104,6 +104,7 @@ struct GroupVTable {
   void (*test_op_sizes)(int op, int* wa, int* wb, int* wo);
   int (*test_op)(int op, const uint32_t* da, const uint32_t* db, uint32_t* dout, size_t n);
   int (*digits_dump)(const void* d_scalars, size_t n, int c, int nwin, uint32_t* dout);
+  int (*batch_scalar_mul)(const void* d_table, const void* d_scalars, size_t n, int c, int nwin, void* d_out, cudaStream_t);
 };
 extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2;
 

@@ -216,8 +216,18 @@ static int run_digits_dump(const void* d_scalars, size_t n, int c, int nwin, uin
   return GMSM_OK;
 }
 
+template <class G>
+static int run_batch_scalar_mul(const void* d_table, const void* d_scalars, size_t n, int c, int nwin, void* d_out, cudaStream_t st) {
+  using F = typename G::F;
+  k_batch_scalar_mul<G><<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(d_table),
+                                                    reinterpret_cast<const typename G::Fr*>(d_scalars), (uint32_t)n, c, nwin,
+                                                    reinterpret_cast<Affine<F>*>(d_out));
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
 #define GMSM_INSTANTIATE(G, NAME)                                                                  \
   const GroupVTable NAME = {&run_window_sums<G>, &run_finalize<G>, &run_generate<G>, &test_op_sizes<G>, \
-                            &run_test_op<G>, &run_digits_dump<G>};
+                            &run_test_op<G>, &run_digits_dump<G>, &run_batch_scalar_mul<G>};
 
 }  // namespace gmsm

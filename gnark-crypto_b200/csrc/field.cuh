@@ -202,7 +202,7 @@ GMSM_HD Fp<P> fp_neg(const Fp<P>& a) {
 // Montgomery multiplication  z = x*y*R^-1 mod q   (F1)
 // ------------------------------------------------------------------------------------------
 template <class P>
-GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
+GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   constexpr int N = P::N;
   Fp<P> r;
 #if defined(__CUDA_ARCH__) && !defined(GMSM_PORTABLE_MUL)
@@ -305,6 +305,26 @@ GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
 #endif
   return r;
 }
+
+// Out-of-line copy of the multiplier (operands and result travel in registers under the device ABI).
+// One mixed add inlines 10 (G1) .. 28 (G2) multiplications of ~220 (N=8) / ~480 (N=12) SASS instructions:
+// 35 .. 100+ KB of straight-line code against a 32 KB L1.5 instruction cache.  GMSM_MUL_NOINLINE trades a
+// CALL/RET pair per multiplication for an instruction footprint that fits.
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp<P> fp_mul_ni(Fp<P> x, Fp<P> y) {
+  return fp_mul_inline(x, y);
+}
+template <class P>
+GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
+  return fp_mul_ni<P>(x, y);
+}
+#else
+template <class P>
+GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
+  return fp_mul_inline(x, y);
+}
+#endif
 
 template <class P>
 GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {

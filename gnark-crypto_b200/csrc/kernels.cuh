@@ -522,6 +522,43 @@ k_generate_multiples(const Affine<typename G::F>* __restrict__ base_p, uint64_t 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// N1: fixed-base batch scalar multiplication (BatchScalarMultiplicationG1, ecc/bn254/g1.go:1039-1118;
+// G2 g2.go:1001+).  table[k] = [k+1]*base in affine (k < 2^(max(c,lastC)-1)); one thread per scalar:
+// signed digits as in partitionScalars, Horner from the top window (c doublings + one mixed add of
+// +-table[|d|-1] per window), then the affine normal form (BatchJacobianToAffineG1's result, :988-1034;
+// here each thread inverts its own ZZZ: x = X*ZZ^2/ZZZ^2, y = Y/ZZZ).
+// ------------------------------------------------------------------------------------------
+static constexpr int BSM_MAX_WINDOWS = 64;   // c >= 4
+template <class G>
+__global__ void __launch_bounds__(128)
+k_batch_scalar_mul(const Affine<typename G::F>* __restrict__ table, const typename G::Fr* __restrict__ scalars, uint32_t n,
+                   int c, int nwin, Affine<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t codes[BSM_MAX_WINDOWS];
+  typename G::Fr s = load_vec_ro(scalars + i);
+  for_each_digit<G>(s, c, nwin, [&](int j, uint32_t code) { codes[j] = code; });
+  XYZZ<F> p = XYZZ<F>::inf();
+  for (int j = nwin - 1; j >= 0; j--) {
+    if (j != nwin - 1)
+      for (int l = 0; l < c; l++) p = xyzz_double_cold(p);
+    const uint32_t code = codes[j];
+    if (code == 0) continue;
+    Affine<F> t = load_vec_ro(table + code_bucket(code));
+    xyzz_add_mixed(p, t, (code & 1u) != 0);
+  }
+  Affine<F> a = Affine<F>::inf();
+  if (!p.is_inf()) {
+    F i3 = f_inv(p.zzz);
+    F i2 = f_mul(f_sqr(p.zz), f_sqr(i3));
+    a.x = f_mul(p.x, i2);
+    a.y = f_mul(p.y, i3);
+  }
+  store_vec(out + i, a);
+}
+
 // test hook kernel (element-wise ops are defined in testops.cuh, shared with the host formula check)
 #if defined(__CUDACC__)
 template <class G>

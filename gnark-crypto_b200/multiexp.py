@@ -274,6 +274,19 @@ class Engine:
             pass
 
 
+def BatchScalarMultiplication(curve: str, base, scalars) -> np.ndarray:
+    """BatchScalarMultiplicationG1 / G2 (ecc/bn254/g1.go:1039-1118, g2.go:1001+): multiplies the same
+    base by all scalars; returns the points in affine coordinates, shape (n, 2*words) uint64."""
+    cid = CURVES[curve]
+    w = _words(cid)
+    base = np.ascontiguousarray(base, dtype=np.uint64).reshape(2 * w)
+    scalars = _as_u64(scalars, 4, "scalars")
+    out = np.zeros((scalars.shape[0], 2 * w), dtype=np.uint64)
+    rc = _native.lib().gmsm_batch_scalar_mul(cid, base.ctypes.data, scalars.ctypes.data, scalars.shape[0], out.ctypes.data)
+    _check(rc)
+    return out
+
+
 # ---- test hooks ----
 def test_op(curve: str, op: int, a: np.ndarray, b: np.ndarray, out_words: int) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint32)

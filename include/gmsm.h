@@ -119,6 +119,12 @@ int gmsm_ctx_last_stage_ms(gmsm_ctx_t* ctx, float out_ms[8]);
 int gmsm_generate_multiples_device(gmsm_curve_t curve, const uint64_t* base_affine_host, uint64_t start,
                                    size_t n, void* d_out_points, void* stream);
 
+/* fixed-base batch scalar multiplication (next-row N1): out[i] = [scalars[i]] * base, affine normal form.
+ * Replaces BatchScalarMultiplicationG1 / G2 (ecc/bn254/g1.go:1039-1118, g2.go:1001+), the step before MSM
+ * in kzg.NewSRS (kzg/kzg.go:129).  Host buffers; scalars in Montgomery form like everywhere else. */
+int gmsm_batch_scalar_mul(gmsm_curve_t curve, const uint64_t* base_affine, const uint64_t* scalars, size_t n,
+                          uint64_t* out_points);
+
 /* ---- 5. test hooks: element-wise device functions, used by tests/ to check the sm_100a field and
  * point arithmetic against the oracle.  a, b, out are HOST arrays of n elements each. ---- */
 enum {

@@ -182,3 +182,28 @@ def test_window_sums_and_finalize_compose(accumulate_mode):
         assert np.array_equal(jac[:8], want)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("g", ["bn254_g1", "bn254_g2", "bls12381_g1"])
+def test_batch_scalar_multiplication_fixed_base(g):
+    """next-row N1: BatchScalarMultiplicationG1/G2 (g1.go:1039-1118) -- same base, n scalars, affine out"""
+    pkg = _pkg()
+    G = O.GROUPS[g]
+    base_pt = G.scalar_mul(G.gen, 0xBEEF)
+    base = G.encode_affine([base_pt])[0]
+    n = 600
+    s = cref.random_scalars(g, n, 9)
+    specials = [0, 1, 2, G.fr.q - 1, G.fr.q - 2, (1 << 200) + 12345]
+    s[: len(specials)] = G.encode_scalars(specials)
+    got = pkg.BatchScalarMultiplication(g, base, s)
+    ks = G.decode_scalars(s)
+    for i in list(range(len(specials))) + [17, 100, 333, 599]:
+        assert np.array_equal(got[i], cref.scalar_mul(g, base, ks[i])), i
+    assert not got[0].any()                                   # [0]B = infinity = (0, 0)
+    assert np.array_equal(got[1], base)
+    # consistency with MultiExp: sum_i [s_i]B == MultiExp(got, ones) == [sum s_i]B
+    tot = sum(ks) % G.fr.q
+    A1, J1, A2, J2 = pkg.curve_package(g.split("_")[0])
+    Aff = A1 if g.endswith("g1") else A2
+    res = Aff().MultiExp(got, G.encode_scalars([1] * n), pkg.MultiExpConfig())
+    assert np.array_equal(res.limbs, cref.scalar_mul(g, base, tot))
