@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_msm.py -m gpu -q --timeout=900 -p no:cacheprovider -k "batch_scalar or config1" 2>&1 | tail -5
-for LIB in "" ni; do
+for LIB in ni; do
   for CFG in "bn254_g1 24" "bls12381_g1 23" "bn254_g2 22"; do
     set -- $CFG
     GMSM_LIB=$LIB timeout 300 python bench.py --curve $1 --logn $2 --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/v_${LIB}_$1.json 2>gpurun_out/v.err
