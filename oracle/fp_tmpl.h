@@ -71,33 +71,31 @@ static inline void FP(neg)(FP(t)* z, const FP(t)* x) {
   for (int i = 0; i < NL; i++) q.l[i] = FP(Q)[i];
   FP(sub)(z, &q, x);
 }
-/* CIOS, fp/element.go:470-591 */
+/* Montgomery multiplication.  "No-carry" CIOS with the two carry chains of a row interleaved, the form
+ * of the reference's portable path (ecc/bn254/fp/element_purego.go:46-213; the spare top bit of q makes
+ * the final word addition carry-free, field/generator/config/field_config.go:203-206); same result as the
+ * textbook CIOS _mulGeneric fp/element.go:470-591. */
 static inline void FP(mul)(FP(t)* z, const FP(t)* x, const FP(t)* y) {
-  uint64_t t[NL + 2];
-  for (int i = 0; i < NL + 2; i++) t[i] = 0;
+  uint64_t t[NL];
+  for (int j = 0; j < NL; j++) t[j] = 0;
+#pragma GCC unroll 8
   for (int i = 0; i < NL; i++) {
-    unsigned __int128 c = 0;
-    for (int j = 0; j < NL; j++) {
-      c += (unsigned __int128)x->l[j] * y->l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[NL];
-    t[NL] = (uint64_t)c;
-    t[NL + 1] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * FP(QINV);
-    c = (unsigned __int128)m * FP(Q)[0] + t[0];
-    c >>= 64;
+    const uint64_t yi = y->l[i];
+    unsigned __int128 A = (unsigned __int128)x->l[0] * yi + t[0];
+    const uint64_t m = (uint64_t)A * FP(QINV);
+    unsigned __int128 B = (unsigned __int128)m * FP(Q)[0] + (uint64_t)A;
+    uint64_t ca = (uint64_t)(A >> 64), cb = (uint64_t)(B >> 64);
+#pragma GCC unroll 8
     for (int j = 1; j < NL; j++) {
-      c += (unsigned __int128)m * FP(Q)[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
+      A = (unsigned __int128)x->l[j] * yi + t[j] + ca;
+      ca = (uint64_t)(A >> 64);
+      B = (unsigned __int128)m * FP(Q)[j] + (uint64_t)A + cb;
+      cb = (uint64_t)(B >> 64);
+      t[j - 1] = (uint64_t)B;
     }
-    c += t[NL];
-    t[NL - 1] = (uint64_t)c;
-    t[NL] = t[NL + 1] + (uint64_t)(c >> 64);
+    t[NL - 1] = ca + cb;
   }
-  if (t[NL] != 0 || FP(geq_q)(t)) FP(sub_q)(t);
+  if (FP(geq_q)(t)) FP(sub_q)(t);
   for (int i = 0; i < NL; i++) z->l[i] = t[i];
 }
 static inline void FP(sqr)(FP(t)* z, const FP(t)* x) { FP(mul)(z, x, x); }
