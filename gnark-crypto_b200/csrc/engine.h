@@ -47,6 +47,7 @@ struct gmsm_ctx {
   uint32_t* entries = nullptr;   // max_n * W (+pad)
   uint32_t* digits = nullptr;    // max_n * W, chunk-major (digits[j*n + i])
   void* buckets = nullptr;       // nb_total xyzz
+  void* buckets2 = nullptr;      // scratch buckets of a follow-up batch (pipelined calls), allocated on demand
   void* carries[2] = {nullptr, nullptr};
   uint32_t* carry_ids[2] = {nullptr, nullptr};
   void* seg[2] = {nullptr, nullptr};
@@ -99,6 +100,8 @@ static inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1
 // heavy template instantiations compile in parallel
 struct GroupVTable {
   int (*window_sums)(gmsm_ctx*, const void* d_points, const void* d_scalars, size_t n, void* d_partials, cudaStream_t);
+  int (*accumulate)(gmsm_ctx*, const void* d_points, const void* d_scalars, size_t n, int rmw, cudaStream_t);
+  int (*bucket_reduce)(gmsm_ctx*, void* d_partials, cudaStream_t);
   int (*finalize)(gmsm_ctx*, const void* d_partials, int nranks, void* d_out, cudaStream_t);
   int (*generate)(const void* d_base, uint64_t start, size_t n, void* d_out, cudaStream_t);
   void (*test_op_sizes)(int op, int* wa, int* wb, int* wo);

@@ -8,10 +8,11 @@ namespace gmsm {
 
 #define LAUNCH_CHECK() CK(cudaGetLastError())
 
-// per-window partial sums -> d_partials (W xyzz)
+// stages K1..K2b on one batch of (points, scalars): afterwards c->buckets holds the bucket sums.
+// rmw = 0: buckets are (re)initialised by this batch; rmw = 1: the batch is accumulated on top of the
+// buckets of the previous batches (pipelined one-shot call: H2D of batch k+1 overlaps K1..K2 of batch k).
 template <class G>
-static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scalars, size_t n, void* d_partials,
-                           cudaStream_t st) {
+static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scalars, size_t n, int rmw, cudaStream_t st) {
   using F = typename G::F;
   using X = XYZZ<F>;
   const WindowPlan& p = c->plan;
@@ -19,9 +20,12 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
   const bool prof = c->profiling;
   auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], st); };
   mark(0);
+  // a follow-up batch (rmw) is accumulated into the scratch bucket array and merged at the end, so the
+  // hot loop never carries a read-modify-write (a divergent full add per bucket boundary otherwise)
+  X* buckets = reinterpret_cast<X*>(rmw ? c->buckets2 : c->buckets);
   if (n == 0) {
-    CK(cudaMemsetAsync(d_partials, 0, (size_t)p.nwin * sizeof(X), st));
-    for (int i = 1; i <= 6; i++) mark(i);
+    if (!rmw) CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
+    for (int i = 1; i <= 5; i++) mark(i);
     c->last_launches = 0;
     return GMSM_OK;
   }
@@ -29,7 +33,6 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
   const size_t nbp = (size_t)p.nb_total + 1;
   const auto* scalars = reinterpret_cast<const typename G::Fr*>(d_scalars);
   const auto* points = reinterpret_cast<const Affine<F>*>(d_points);
-  X* buckets = reinterpret_cast<X*>(c->buckets);
 
   // K1: digits + histogram
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
@@ -63,6 +66,7 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
     LAUNCH_CHECK();
   }
   mark(3);
+  if (c->affine && rmw) return set_err(GMSM_EINVAL, "internal: batch-affine accumulation cannot extend existing buckets");
   if (c->affine) {
     // K2 (batch-affine): balanced tree over the bucket-ordered entries, one shared inversion per level
     using A = Affine<F>;
@@ -132,7 +136,7 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
     CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
     {
       k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
-                                                          buckets, reinterpret_cast<X*>(c->carries[0]), c->carry_ids[0], 0);
+                                                          buckets, reinterpret_cast<X*>(c->carries[0]), c->carry_ids[0]);
       launches++;
       LAUNCH_CHECK();
     }
@@ -153,8 +157,26 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
       }
     }
   }
+  if (rmw) {
+    k_merge_buckets<G><<<nblk(p.nb_total, 128), 128, 0, st>>>(reinterpret_cast<X*>(c->buckets), buckets, p.nb_total);
+    launches++;
+    LAUNCH_CHECK();
+  }
   mark(5);
-  // K3: bucket reduction
+  c->last_launches = launches;
+  return GMSM_OK;
+}
+
+// stage K3: bucket reduction of c->buckets -> W window partials
+template <class G>
+static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
+  using F = typename G::F;
+  using X = XYZZ<F>;
+  const WindowPlan& p = c->plan;
+  int launches = 0;
+  const bool prof = c->profiling;
+  auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], st); };
+  X* buckets = reinterpret_cast<X*>(c->buckets);
   {
     const uint32_t S = c->seg_S, L = c->seg_L;
     k_bucket_segments<G><<<nblk((size_t)p.nwin * S, 128), 128, 0, st>>>(buckets, p.nwin, p.nb, p.nb_last, L, S,
@@ -179,8 +201,16 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
     }
   }
   mark(6);
-  c->last_launches = launches;
+  c->last_launches += launches;
   return GMSM_OK;
+}
+
+// per-window partial sums of one batch -> d_partials (W xyzz)
+template <class G>
+static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scalars, size_t n, void* d_partials,
+                           cudaStream_t st) {
+  if (int rc = run_accumulate<G>(c, d_points, d_scalars, n, 0, st)) return rc;
+  return run_bucket_reduce<G>(c, d_partials, st);
 }
 
 template <class G>
@@ -227,7 +257,7 @@ static int run_batch_scalar_mul(const void* d_table, const void* d_scalars, size
 }
 
 #define GMSM_INSTANTIATE(G, NAME)                                                                  \
-  const GroupVTable NAME = {&run_window_sums<G>, &run_finalize<G>, &run_generate<G>, &test_op_sizes<G>, \
+  const GroupVTable NAME = {&run_window_sums<G>, &run_accumulate<G>, &run_bucket_reduce<G>, &run_finalize<G>, &run_generate<G>, &test_op_sizes<G>, \
                             &run_test_op<G>, &run_digits_dump<G>, &run_batch_scalar_mul<G>};
 
 }  // namespace gmsm

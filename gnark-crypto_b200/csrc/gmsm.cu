@@ -144,7 +144,7 @@ static int ctx_alloc(gmsm_ctx* c) {
 
 static void ctx_free(gmsm_ctx* c) {
   cudaSetDevice(c->device);
-  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->buckets);
+  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->buckets2); cudaFree(c->buckets);
   for (int i = 0; i < 2; i++) { cudaFree(c->carries[i]); cudaFree(c->carry_ids[i]); cudaFree(c->seg[i]); }
   cudaFree(c->win_partials); cudaFree(c->fin_scratch);
   for (int i = 0; i < 2; i++) { cudaFree(c->aff_buf[i]); cudaFree(c->aff_off[i]); }
@@ -262,20 +262,128 @@ extern "C" int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const 
 // ------------------------------------------------------------------------------------------
 // resident bases + one-shot host API
 // ------------------------------------------------------------------------------------------
-struct gmsm_bases {
-  int curve;
-  int device;
-  size_t n;
-  size_t cap = 0;
-  void* d_points;
-  // per-bases engine state (lazy): scalar staging + ctx sized for the largest request so far
+// A pipelined MSM over host scalars (and optionally host points): the inputs are cut into S contiguous
+// batches; batch k+1 crosses PCIe on the copy stream while batch k runs K1..K2b on the compute stream,
+// every batch accumulating into the same bucket array (rmw); one bucket reduction + finalize at the end.
+struct Pipeline {
+  int curve = 0, device = 0;
   gmsm_ctx* ctx = nullptr;
   void* d_scalars = nullptr;
-  size_t scalars_cap = 0;
+  size_t scal_cap = 0;
+  void* d_partials = nullptr;
+  int partials_cap = 0;
   void* d_out = nullptr;
-  cudaStream_t stream = nullptr;
-  std::mutex mu;
+  cudaStream_t copy_st = nullptr, comp_st = nullptr;
+  cudaEvent_t ev[16] = {};
+  int last_launches = 0;
 };
+
+static int pipeline_init(Pipeline& P, int curve, int device) {
+  if (P.copy_st) return GMSM_OK;
+  P.curve = curve; P.device = device;
+  CK(cudaStreamCreateWithFlags(&P.copy_st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&P.comp_st, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&P.ev[i], cudaEventDisableTiming));
+  CK(cudaMalloc(&P.d_out, 512));
+  return GMSM_OK;
+}
+
+static void pipeline_free(Pipeline& P) {
+  if (P.ctx) gmsm_ctx_destroy(P.ctx);
+  cudaFree(P.d_scalars); cudaFree(P.d_partials); cudaFree(P.d_out);
+  if (P.copy_st) cudaStreamDestroy(P.copy_st);
+  if (P.comp_st) cudaStreamDestroy(P.comp_st);
+  for (int i = 0; i < 16; i++) if (P.ev[i]) cudaEventDestroy(P.ev[i]);
+  P = Pipeline();
+}
+
+// d_points: device buffer holding (resident) or receiving (h_points != nullptr) the n points
+static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, const uint64_t* h_scalars, size_t n,
+                        uint64_t* out_jac) {
+  CurveInfo ci;
+  curve_info(P.curve, &ci);
+  const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
+  CK(cudaSetDevice(P.device));
+  // batch sizes grow geometrically (1/16, 1/8, 3/16, 1/4, 3/8 of n): the first copy is short, and since the
+  // GPU consumes a batch more slowly than PCIe delivers the next, every later copy hides under compute
+  static const int FR5[5] = {1, 2, 3, 4, 6};   // sixteenths
+  int nch = (n >= (1u << 21)) ? 5 : ((n >= (1u << 18)) ? 2 : 1);
+  if (const char* e = getenv("GMSM_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) nch = v; }
+  if ((size_t)nch > n) nch = 1;
+  size_t bstart[17];
+  bstart[0] = 0;
+  for (int k = 1; k <= nch; k++) {
+    if (nch == 5) { int acc16 = 0; for (int u = 0; u < k; u++) acc16 += FR5[u]; bstart[k] = (k == nch) ? n : (n / 16) * acc16; }
+    else bstart[k] = (k == nch) ? n : (n / nch) * k;
+  }
+  size_t nc = 0;
+  for (int k = 0; k < nch; k++) nc = std::max(nc, bstart[k + 1] - bstart[k]);
+  if (P.scal_cap < n || P.scal_cap > 4 * n + 1024) {
+    cudaFree(P.d_scalars); P.d_scalars = nullptr; P.scal_cap = 0;
+    CK(cudaMalloc(&P.d_scalars, n * 32));
+    P.scal_cap = n;
+  }
+  // window width from the TOTAL size (all batches share one bucket array); workspace sized for one batch
+  const int c = choose_c(ci.fr_bits, n);
+  if (!P.ctx || P.ctx->max_n < nc || P.ctx->max_n > 4 * nc + 1024 || P.ctx->plan.c != c) {
+    if (P.ctx) { gmsm_ctx_destroy(P.ctx); P.ctx = nullptr; }
+    P.ctx = gmsm_ctx_create((gmsm_curve_t)P.curve, nc, c, P.device);
+    if (!P.ctx) return GMSM_ECUDA;
+  }
+  if (P.partials_cap < nch * P.ctx->plan.nwin) {
+    cudaFree(P.d_partials); P.d_partials = nullptr;
+    CK(cudaMalloc(&P.d_partials, (size_t)nch * P.ctx->plan.nwin * xb));
+    P.partials_cap = nch * P.ctx->plan.nwin;
+  }
+  const GroupVTable* vt = vtable(P.curve);
+  const char* hp = reinterpret_cast<const char*>(h_points);
+  const char* hs = reinterpret_cast<const char*>(h_scalars);
+  const bool shared_buckets = !P.ctx->affine;   // the batch-affine path keeps per-batch partials instead
+  if (shared_buckets && nch > 1 && !P.ctx->buckets2) {
+    CK(cudaMalloc(&P.ctx->buckets2, (size_t)P.ctx->plan.nb_total * xb));
+  }
+  int launches = 0;
+  std::lock_guard<std::mutex> lk(P.ctx->mu);
+  for (int k = 0; k < nch; k++) {
+    const size_t off = bstart[k];
+    const size_t m = bstart[k + 1] - off;
+    CK(cudaMemcpyAsync((char*)P.d_scalars + off * 32, hs + off * 32, m * 32, cudaMemcpyHostToDevice, P.copy_st));
+    if (hp) CK(cudaMemcpyAsync((char*)d_points + off * ab, hp + off * ab, m * ab, cudaMemcpyHostToDevice, P.copy_st));
+    CK(cudaEventRecord(P.ev[k], P.copy_st));
+    CK(cudaStreamWaitEvent(P.comp_st, P.ev[k], 0));
+    int rc;
+    if (shared_buckets) {
+      rc = vt->accumulate(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m, k > 0, P.comp_st);
+    } else {
+      rc = vt->window_sums(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m,
+                           (char*)P.d_partials + (size_t)k * P.ctx->plan.nwin * xb, P.comp_st);
+    }
+    if (rc) return rc;
+    launches += P.ctx->last_launches;
+  }
+  if (shared_buckets) {
+    P.ctx->last_launches = 0;
+    if (int rc = vt->bucket_reduce(P.ctx, P.d_partials, P.comp_st)) return rc;
+    launches += P.ctx->last_launches;
+    if (int rc = vt->finalize(P.ctx, P.d_partials, 1, P.d_out, P.comp_st)) return rc;
+  } else {
+    if (int rc = vt->finalize(P.ctx, P.d_partials, nch, P.d_out, P.comp_st)) return rc;
+  }
+  P.last_launches = launches + 1;
+  CK(cudaMemcpyAsync(out_jac, P.d_out, jb, cudaMemcpyDeviceToHost, P.comp_st));
+  CK(cudaStreamSynchronize(P.comp_st));
+  CK(cudaStreamSynchronize(P.copy_st));
+  g_last_oneshot_launches = P.last_launches;
+  return GMSM_OK;
+}
+
+static int check_device(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return set_err(GMSM_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  return GMSM_OK;
+}
 
 static int check_nb_tasks(int nb_tasks) {
   // (*G1Jac).MultiExp, multiexp.go:67-71
@@ -283,55 +391,36 @@ static int check_nb_tasks(int nb_tasks) {
   return GMSM_OK;
 }
 
-extern "C" void gmsm_bases_free(gmsm_bases_t* b);
-
-// allocate an (empty) resident-bases object with room for `cap` points
-static gmsm_bases* bases_alloc(int curve, size_t cap, int device) {
-  CurveInfo ci;
-  if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) { set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
-  if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range", device); return nullptr; }
-  cudaSetDevice(device);
-  gmsm_bases* b = new gmsm_bases();
-  b->curve = curve; b->device = device; b->n = 0; b->cap = cap;
-  size_t bytes = cap * 8u * ci.coord_words;
-  if (cudaMalloc(&b->d_points, bytes ? bytes : 16) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc(%zu) for bases failed", bytes); delete b; return nullptr; }
-  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(GMSM_ECUDA, "stream create failed"); cudaFree(b->d_points); delete b; return nullptr; }
-  if (cudaMalloc(&b->d_out, 12u * ci.coord_words) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc out"); cudaFree(b->d_points); cudaStreamDestroy(b->stream); delete b; return nullptr; }
-  return b;
-}
-
-// asynchronous H2D of n points into the object (ordered on its stream before the next multiexp)
-static int bases_fill(gmsm_bases* b, const uint64_t* points, size_t n) {
-  CurveInfo ci;
-  curve_info(b->curve, &ci);
-  if (n > b->cap) return set_err(GMSM_EINVAL, "internal: bases capacity");
-  CK(cudaSetDevice(b->device));
-  if (n) CK(cudaMemcpyAsync(b->d_points, points, n * 8u * ci.coord_words, cudaMemcpyHostToDevice, b->stream));
-  b->n = n;
-  return GMSM_OK;
-}
+// ---- resident bases ----
+struct gmsm_bases {
+  int curve = 0, device = 0;
+  size_t n = 0;
+  void* d_points = nullptr;
+  Pipeline pipe;
+  std::mutex mu;
+};
 
 extern "C" gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size_t n, int device) {
-  gmsm_bases* b = bases_alloc(curve, n, device);
-  if (!b) return nullptr;
-  if (bases_fill(b, points, n) != GMSM_OK || cudaStreamSynchronize(b->stream) != cudaSuccess) {
-    std::string keep = g_err.empty() ? std::string("H2D copy of bases failed") : g_err;
-    gmsm_bases_free(b);
-    g_err = keep;
-    return nullptr;
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
+  if (check_device(device) != GMSM_OK) return nullptr;
+  cudaSetDevice(device);
+  gmsm_bases* b = new gmsm_bases();
+  b->curve = curve; b->device = device; b->n = n;
+  const size_t bytes = n * 8u * ci.coord_words;
+  if (cudaMalloc(&b->d_points, bytes ? bytes : 16) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc(%zu) for bases failed", bytes); delete b; return nullptr; }
+  if (bytes && cudaMemcpy(b->d_points, points, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_err(GMSM_ECUDA, "H2D copy of bases failed"); cudaFree(b->d_points); delete b; return nullptr;
   }
+  if (pipeline_init(b->pipe, curve, device) != GMSM_OK) { cudaFree(b->d_points); delete b; return nullptr; }
   return b;
 }
 
 extern "C" void gmsm_bases_free(gmsm_bases_t* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  if (b->ctx) gmsm_ctx_destroy(b->ctx);
-  cudaFree(b->d_points); cudaFree(b->d_scalars); cudaFree(b->d_out);
-  if (b->stream) cudaStreamDestroy(b->stream);
+  pipeline_free(b->pipe);
+  cudaFree(b->d_points);
   delete b;
 }
 
@@ -341,29 +430,11 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   if (int rc = check_nb_tasks(nb_tasks)) return rc;
   if (offset > b->n || n > b->n - offset) return set_err(GMSM_EINVAL, "len(points) != len(scalars)");
   std::lock_guard<std::mutex> lk(b->mu);
-  CK(cudaSetDevice(b->device));
   CurveInfo ci;
   curve_info(b->curve, &ci);
-  const size_t jac_bytes = 12u * ci.coord_words;
-  if (n == 0) { memset(out_jac, 0, jac_bytes); return GMSM_OK; }
-  // engine sized to the request (window width depends on n); re-created when n grows or shrinks 4x
-  if (!b->ctx || b->ctx->max_n < n || b->ctx->max_n > 4 * n) {
-    if (b->ctx) { gmsm_ctx_destroy(b->ctx); b->ctx = nullptr; }
-    b->ctx = gmsm_ctx_create((gmsm_curve_t)b->curve, n, 0, b->device);
-    if (!b->ctx) return GMSM_ECUDA;
-  }
-  if (b->scalars_cap < n) {
-    cudaFree(b->d_scalars); b->d_scalars = nullptr; b->scalars_cap = 0;
-    CK(cudaMalloc(&b->d_scalars, n * 32));
-    b->scalars_cap = n;
-  }
-  CK(cudaMemcpyAsync(b->d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, b->stream));
-  const char* pts = reinterpret_cast<const char*>(b->d_points) + offset * 8u * ci.coord_words;
-  int rc = gmsm_ctx_msm_device(b->ctx, pts, b->d_scalars, n, b->d_out, b->stream);
-  if (rc != GMSM_OK) return rc;
-  CK(cudaMemcpyAsync(out_jac, b->d_out, jac_bytes, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
-  return GMSM_OK;
+  if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
+  char* pts = reinterpret_cast<char*>(b->d_points) + offset * 8u * ci.coord_words;
+  return pipeline_run(b->pipe, pts, nullptr, scalars, n, out_jac);
 }
 
 extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
@@ -371,88 +442,25 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   if (int rc = check_nb_tasks(nb_tasks)) return rc;
   CurveInfo ci;
   if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
-  if (n == 0) {
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) return set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
-    memset(out_jac, 0, 12u * ci.coord_words);
-    return GMSM_OK;
-  }
   int device = 0;
   if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
-  {
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) return set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
-    if (device < 0 || device >= ndev) return set_err(GMSM_EINVAL, "device %d out of range", device);
-  }
-  // Per-(curve, device) session: device buffers, streams and the engine context are kept between
-  // calls (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc.
-  // The call is pipelined: the inputs are cut into S contiguous chunks; chunk k+1 crosses PCIe on the
-  // copy stream while chunk k runs K1..K3 on the compute stream (each chunk is an independent
-  // sub-MSM producing W window partials -- the same decomposition as the multi-GPU path and as the
-  // reference's recursive halving, multiexp.go:128-140); one finalize joins the S x W partials.
-  struct Session {
-    size_t cap = 0, chunk_cap = 0;
-    int nchunks_cap = 0;
-    void *d_points = nullptr, *d_scalars = nullptr, *d_partials = nullptr, *d_out = nullptr;
-    gmsm_ctx* ctx = nullptr;
-    cudaStream_t copy_st = nullptr, comp_st = nullptr;
-    cudaEvent_t ev[16] = {};
-  };
+  if (int rc = check_device(device)) return rc;
+  if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
+  // per-(curve, device) session: device buffers, streams and the engine context are kept between calls
+  // (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
+  struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; };
   static std::mutex sess_mu;
   static std::map<std::pair<int, int>, Session> sessions;
   std::lock_guard<std::mutex> lk(sess_mu);
   CK(cudaSetDevice(device));
   Session& S = sessions[std::make_pair((int)curve, device)];
-  const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
-  int nch = (n >= (1u << 21)) ? 4 : 1;
-  if (const char* e = getenv("GMSM_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) nch = v; }
-  if ((size_t)nch > n) nch = 1;
-  const size_t nc = (n + nch - 1) / nch;
-  if (!S.copy_st) {
-    CK(cudaStreamCreateWithFlags(&S.copy_st, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&S.comp_st, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming));
-    CK(cudaMalloc(&S.d_out, 512));
-  }
+  if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
   if (S.cap < n || S.cap > 4 * n + 1024) {
-    cudaFree(S.d_points); cudaFree(S.d_scalars); S.d_points = S.d_scalars = nullptr; S.cap = 0;
-    CK(cudaMalloc(&S.d_points, n * ab));
-    CK(cudaMalloc(&S.d_scalars, n * 32));
+    cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
+    CK(cudaMalloc(&S.d_points, n * 8u * ci.coord_words));
     S.cap = n;
   }
-  if (!S.ctx || S.ctx->max_n < nc || S.ctx->max_n > 4 * nc + 1024 || S.nchunks_cap < nch) {
-    if (S.ctx) { gmsm_ctx_destroy(S.ctx); S.ctx = nullptr; }
-    cudaFree(S.d_partials); S.d_partials = nullptr;
-    S.ctx = gmsm_ctx_create(curve, nc, 0, device);
-    if (!S.ctx) return GMSM_ECUDA;
-    CK(cudaMalloc(&S.d_partials, (size_t)nch * S.ctx->plan.nwin * xb));
-    S.nchunks_cap = nch;
-  }
-  const GroupVTable* vt = vtable(curve);
-  const char* hp = reinterpret_cast<const char*>(points);
-  const char* hs = reinterpret_cast<const char*>(scalars);
-  int launches = 0;
-  for (int k = 0; k < nch; k++) {
-    const size_t off = (size_t)k * nc;
-    const size_t m = std::min(nc, n - off);
-    CK(cudaMemcpyAsync((char*)S.d_scalars + off * 32, hs + off * 32, m * 32, cudaMemcpyHostToDevice, S.copy_st));
-    CK(cudaMemcpyAsync((char*)S.d_points + off * ab, hp + off * ab, m * ab, cudaMemcpyHostToDevice, S.copy_st));
-    CK(cudaEventRecord(S.ev[k], S.copy_st));
-    CK(cudaStreamWaitEvent(S.comp_st, S.ev[k], 0));
-    std::lock_guard<std::mutex> lk2(S.ctx->mu);
-    if (int rc = vt->window_sums(S.ctx, (char*)S.d_points + off * ab, (char*)S.d_scalars + off * 32, m,
-                                 (char*)S.d_partials + (size_t)k * S.ctx->plan.nwin * xb, S.comp_st)) return rc;
-    launches += S.ctx->last_launches;
-  }
-  if (int rc = vt->finalize(S.ctx, S.d_partials, nch, S.d_out, S.comp_st)) return rc;
-  S.ctx->last_launches = launches + 1;
-  CK(cudaMemcpyAsync(out_jac, S.d_out, jb, cudaMemcpyDeviceToHost, S.comp_st));
-  CK(cudaStreamSynchronize(S.comp_st));
-  CK(cudaStreamSynchronize(S.copy_st));
-  g_last_oneshot_launches = S.ctx->last_launches;
-  return GMSM_OK;
+  return pipeline_run(S.pipe, S.d_points, points, scalars, n, out_jac);
 }
 
 extern "C" int gmsm_bn254_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_BN254_G1, p, s, n, t, out); }

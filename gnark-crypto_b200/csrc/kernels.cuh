@@ -259,7 +259,7 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 // reference needs chunkStat weights and a two-goroutine split for skewed windows, multiexp.go:185-203).
 // A thread keeps the running bucket sum in registers (extended Jacobian, mixed adds with the
 // reference's exact special cases) and flushes it at each bucket boundary:
-//   * bucket begins inside the chunk  -> the thread owns it: buckets[b] = sum (or += in rmw mode)
+//   * bucket begins inside the chunk  -> the thread owns it: buckets[b] = sum
 //   * bucket began in an earlier chunk -> the partial goes to carries[t] (joined by k_carry_level)
 // ------------------------------------------------------------------------------------------
 template <class G>
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : 1)
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
              XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,
-             uint32_t* __restrict__ carry_ids, int rmw) {
+             uint32_t* __restrict__ carry_ids) {
   using F = typename G::F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
@@ -300,13 +300,7 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
     if (pos == bend) {
       // bucket boundary: flush, move to the bucket that contains `pos`
       if (owner) {
-        if (rmw) {
-          XYZZ<F> old = load_vec(buckets + b);
-          xyzz_add_cold(old, acc);
-          store_vec(buckets + b, old);
-        } else {
-          store_vec(buckets + b, acc);
-        }
+        store_vec(buckets + b, acc);
       } else {
         store_vec(carries + t, acc);
         my_carry = b;
@@ -324,13 +318,7 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
     }
   }
   if (owner) {
-    if (rmw) {
-      XYZZ<F> old = load_vec(buckets + b);
-      xyzz_add_cold(old, acc);
-      store_vec(buckets + b, old);
-    } else {
-      store_vec(buckets + b, acc);
-    }
+    store_vec(buckets + b, acc);
   } else {
     store_vec(carries + t, acc);
     my_carry = b;
@@ -381,6 +369,20 @@ k_carry_level(const XYZZ<typename G::F>* __restrict__ in_pts, const uint32_t* __
     }
   }
   out_ids[t] = out_id;
+}
+
+// dst[b] += src[b] for every bucket (joins the buckets of a pipelined batch into the running ones)
+template <class G>
+__global__ void __launch_bounds__(128)
+k_merge_buckets(XYZZ<typename G::F>* __restrict__ dst, const XYZZ<typename G::F>* __restrict__ src, uint32_t nb) {
+  using F = typename G::F;
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  XYZZ<F> q = load_vec(src + b);
+  if (q.is_inf()) return;
+  XYZZ<F> p = load_vec(dst + b);
+  xyzz_add_cold(p, q);
+  store_vec(dst + b, p);
 }
 
 // ------------------------------------------------------------------------------------------
