@@ -276,8 +276,12 @@ def main():
     A = AFF_BYTES[g]
     alg_bytes = n * W * (A + 2)             # per (point, window): one affine point + one u16 digit
     achieved = alg_bytes / (acc * 1e-3) / 1e9
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("%s:%d:%d" % (g, args.logn, c))
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": acc,
                 "alg_bytes_per_launch": alg_bytes,
                 "int_pipe": {"mixed_adds_per_s": n * W / (acc * 1e-3), "note": "INT32-pipe bound: ~10 modmul (~1.4k IMAD.WIDE) per 66 B"}}
     stage_names = ["digits_hist", "scan", "scatter", "accumulate", "carries", "bucket_reduce", "finalize", "total"]
@@ -319,9 +323,7 @@ def main():
             ds2 = torch.empty(n * 4, dtype=torch.int64, device=d_points.device)
 
             def e2e_step():
-                dp2.copy_(h_points, non_blocking=True)
-                ds2.copy_(h_scal, non_blocking=True)
-                return sharded.msm(dp2, ds2, n).cpu().numpy().view(np.uint64)
+                return sharded.msm_from_host(h_points, h_scal, n, dp2, ds2, chunks=4).cpu().numpy().view(np.uint64)
         for _ in range(2):
             r = e2e_step()
         barrier()
@@ -339,7 +341,7 @@ def main():
         line["e2e"] = {"value": n_total / dt, "unit": "scalar-muls/s", "ms_per_step": dt * 1e3,
                        "h2d_bytes_per_step": n_total * (A + 32), "d2h_bytes_per_step": jac_words * 8 * world,
                        "path": "gmsm_multiexp one-shot (points+scalars H2D every call)" if world == 1 else
-                               "pinned host shards -> H2D -> sharded MultiExp -> D2H"}
+                               "pinned host shards -> chunked H2D overlapped with the bucket pass -> NCCL all-gather of partials -> finalize -> D2H"}
         if world == 1:
             launches_e2e = native.lib().gmsm_last_oneshot_launches()
             line["gpu_launches"] += launches_e2e * args.steps

@@ -57,7 +57,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   mark(2);
   // K1c: scatter, one launch per window (L2-resident write set)
   {
-    unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
+    unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 8u);
     for (int j = 0; j < p.nwin; j++) {
       k_scatter_window<<<blocks, 256, 0, st>>>(c->digits + (size_t)j * n, n32, c->hist + (size_t)j * p.nb,
                                                c->offsets + (size_t)j * p.nb, c->entries);

@@ -142,13 +142,33 @@ __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32
 // full lines, instead of one read-modify-write per 4-byte store.  Entries of a bucket are filled from
 // the back: pos = offsets[b] + (old count - 1); the histogram counts down to zero.
 static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t* __restrict__ hist_w,
-                                 const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t code = __ldg(digits_w + i);
-    if (code == 0) continue;
-    uint32_t b = code_bucket(code);
-    uint32_t old = atomicSub(&hist_w[b], 1u);
-    entries[offsets_w[b] + old - 1u] = (i << 1) | (code & 1u);
+                                        const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries) {
+  // 4 independent elements per thread and iteration: the kernel is bound by the round trip of the
+  // returning atomics (ncu: long_scoreboard 324 per issue with one in flight), so keep 4 in flight
+  constexpr int U = 4;
+  const uint32_t tile = blockDim.x * U;
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n; base += (uint64_t)gridDim.x * tile) {
+    uint32_t code[U], old[U], off[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+      code[u] = (i < n) ? __ldg(digits_w + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t b = code_bucket(code[u]);
+        old[u] = atomicSub(&hist_w[b], 1u);
+        off[u] = offsets_w[b];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t i = (uint32_t)(base + (uint64_t)u * blockDim.x + threadIdx.x);
+        entries[off[u] + old[u] - 1u] = (i << 1) | (code[u] & 1u);
+      }
+    }
   }
 }
 

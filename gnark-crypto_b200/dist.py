@@ -45,6 +45,31 @@ class ShardedMultiExp:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    def msm_from_host(self, h_points, h_scalars, n_local: int, d_points_buf, d_scalars_buf, chunks: int = 4):
+        """End-to-end sharded MSM from pinned host shards: the shard is cut into `chunks` batches; batch k+1
+        crosses PCIe on a copy stream while batch k runs the bucket pass (each batch yields W window
+        partials); all ranks all-gather their chunks x W partials and finalize over world x chunks groups."""
+        torch = self.engine.torch
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+        main = torch.cuda.current_stream(self.engine.device)
+        self._copy_stream.wait_stream(main)
+        wa = 2 * self.engine.w          # int64 words per affine point
+        pw = self.engine.partials_bytes // 8
+        chunks = max(1, min(chunks, n_local))
+        partials = torch.empty(chunks * pw, dtype=torch.int64, device=d_points_buf.device)
+        for k in range(chunks):
+            lo, hi = n_local * k // chunks, n_local * (k + 1) // chunks
+            with torch.cuda.stream(self._copy_stream):
+                d_scalars_buf[lo * 4 : hi * 4].copy_(h_scalars[lo * 4 : hi * 4], non_blocking=True)
+                d_points_buf[lo * wa : hi * wa].copy_(h_points[lo * wa : hi * wa], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            main.wait_event(ev)
+            self.engine.window_sums(d_points_buf[lo * wa :], d_scalars_buf[lo * 4 :], hi - lo, out=partials[k * pw : (k + 1) * pw])
+        allp = gather_partials(partials, self.world, self.group)
+        return self.engine.finalize(allp, self.world * chunks)
+
     def msm(self, d_points_shard, d_scalars_shard, n_local: int):
         partials = self.engine.window_sums(d_points_shard, d_scalars_shard, n_local)
         allp = gather_partials(partials, self.world, self.group)

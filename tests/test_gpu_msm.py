@@ -207,3 +207,49 @@ def test_batch_scalar_multiplication_fixed_base(g):
     Aff = A1 if g.endswith("g1") else A2
     res = Aff().MultiExp(got, G.encode_scalars([1] * n), pkg.MultiExpConfig())
     assert np.array_equal(res.limbs, cref.scalar_mul(g, base, tot))
+
+
+@pytest.mark.parametrize("g,n", [("bn254_g1", (1 << 19) + 3), ("bn254_g1", (1 << 21) + 17), ("bls12381_g1", (1 << 18) + 1),
+                                 ("bn254_g2", (1 << 18) + 5)])
+def test_pipelined_host_calls_closed_form(g, n):
+    """the host entry points cut large inputs into batches that share one bucket array (H2D of batch k+1
+    under the bucket pass of batch k; scratch buckets + merge): one-shot gmsm_multiexp and resident bases
+    must both give [sum (i+1) s_i] B, and ragged n must work"""
+    from importlib import import_module
+
+    pkg = _pkg()
+    mx = import_module("gnark-crypto_b200.multiexp")
+    G = O.GROUPS[g]
+    base = G.encode_affine([G.scalar_mul(G.gen, 0xABCDEF)])[0]
+    eng = pkg.Engine(g, n, c=0)
+    try:
+        w = base.size
+        pts = eng.generate_multiples(base, 1, n).cpu().numpy().view(np.uint64).reshape(n, w)
+    finally:
+        eng.close()
+    s = cref.random_scalars(g, n, 2024)
+    want = cref.scalar_mul(g, base, cref.dot_index(g, s, 1))
+    A1, J1, A2, J2 = pkg.curve_package(g.split("_")[0])
+    Aff = A1 if g.endswith("g1") else A2
+    got = Aff().MultiExp(pts, s, pkg.MultiExpConfig())
+    assert np.array_equal(got.limbs, want)
+    rb = mx.ResidentBases(g, pts)
+    try:
+        assert np.array_equal(rb.MultiExp(s)[:w], want)
+        # a second call on the same handle with fewer scalars (context reuse / shrink path)
+        m = n // 3
+        want2 = cref.scalar_mul(g, base, cref.dot_index(g, s[:m], 1))
+        assert np.array_equal(rb.MultiExp(s[:m])[:w], want2)
+    finally:
+        rb.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 33, 257])
+def test_tiny_and_ragged_sizes(n):
+    g = "bn254_g1"
+    pkg = _pkg()
+    pts, s = make_inputs(g, max(n, 64), 5, specials=False)
+    pts, s = pts[:n], s[:n]
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=1)
+    got = pkg.G1Affine().MultiExp(pts, s, pkg.MultiExpConfig())
+    assert np.array_equal(got.limbs, want)
