@@ -253,3 +253,38 @@ def test_tiny_and_ragged_sizes(n):
     want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=1)
     got = pkg.G1Affine().MultiExp(pts, s, pkg.MultiExpConfig())
     assert np.array_equal(got.limbs, want)
+
+
+def test_kzg_commit_over_generated_srs_and_dump_roundtrip(tmp_path):
+    """next-row N2 on top of N1: SRS = [alpha^i]G by BatchScalarMultiplication (kzg.NewSRS, kzg.go:129),
+    raw dump (marker + unsafe.WriteSlice image) -> resident bases, Commit(f) == [f(alpha)]G
+    (TestCommit, ecc/bn254/kzg/kzg_test.go:209-239)"""
+    from importlib import import_module
+
+    kzg = import_module("gnark-crypto_b200.kzg")
+    g = "bn254_g1"
+    G = O.GROUPS[g]
+    r = G.fr.q
+    size, alpha = 3000, 0x1234567890ABCDEF1234567
+    gen = G.encode_affine([G.gen])[0]
+    srs = kzg.new_srs_g1("bn254", size, alpha, gen, r, G.encode_scalars)
+    assert np.array_equal(srs[0], gen) and np.array_equal(srs[1], cref.scalar_mul(g, gen, alpha))
+    path = tmp_path / "srs.dump"
+    with open(path, "wb") as f:
+        f.write(b"\x00" * 40)                      # stands in for the verifying-key prefix
+        kzg.write_marker(f)
+        kzg.write_slice(f, srs)
+    with open(path, "rb") as f:
+        f.seek(40)
+        pk = kzg.ProvingKey.from_dump("bn254", f, max_pk_points=2048)
+    assert pk.G1.shape == (2048, 8) and np.array_equal(pk.G1, srs[:2048])
+    rng = np.random.default_rng(3)
+    coeffs = [int(x) for x in rng.integers(0, 2**62, size=2000)]
+    f_alpha = sum(c * pow(alpha, i, r) for i, c in enumerate(coeffs)) % r
+    digest = kzg.Commit(G.encode_scalars(coeffs), pk)
+    assert np.array_equal(digest, cref.scalar_mul(g, gen, f_alpha))
+    with pytest.raises(kzg.ErrInvalidPolynomialSize):
+        kzg.Commit(G.encode_scalars([1] * 2049), pk)
+    with pytest.raises(kzg.ErrInvalidPolynomialSize):
+        kzg.Commit(np.zeros((0, 4), dtype=np.uint64), pk)
+    pk.close()
