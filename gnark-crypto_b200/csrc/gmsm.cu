@@ -77,9 +77,15 @@ static int choose_c(int fr_bits, size_t n) {
     int c = atoi(e);
     if (c >= 2 && c <= 24) return c;
   }
+  // Measured on B200 (profiles/r01_c_sweep_all_v6.txt: bn254 G1 2^16..2^24, bls12-381 G1 2^22, bn254 G2
+  // 2^20/2^22): c = 17 (W = 15, lastC = 17) wins from n = 2^20 up for every group, c = 15 for 2^16..2^18;
+  // c = 18 keeps W = 15 but doubles the bucket reduction.  Below that the launch-latency floor (~3 ms)
+  // dominates and the analytic model is good enough.
+  if (n >= ((size_t)1 << 19)) return 17;
+  if (n >= ((size_t)1 << 14)) return 15;
   double best = 1e300;
   int bc = 8;
-  for (int c = 4; c <= 22; c++) {
+  for (int c = 4; c <= 16; c++) {
     WindowPlan p = make_plan(fr_bits, c);
     double acc = (double)p.nwin * (double)n;
     double red = (double)p.nb_total * (2.0 + 22.0 / 32.0) * 1.4 * 3.0;
