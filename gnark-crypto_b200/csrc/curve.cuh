@@ -148,6 +148,37 @@ GMSM_HD void xyzz_add(XYZZ<F>& p, const XYZZ<F>& q) {
   p.zzz = f_mul(f_mul(p.zzz, q.zzz), PPP);
 }
 
+// Jacobian doubling for a = 0 (dbl-2009-l: 2M + 5S; the reference's G1Jac.DoubleAssign, g1.go:396-424, is the
+// same point in the same coordinate system).  Valid for infinity (Z = 0 stays 0).  Used by the serial Horner
+// of k_finalize, where it replaces the 6M + 3S extended-Jacobian doubling.
+template <class F>
+GMSM_HD Jac<F> jac_double(const Jac<F>& p) {
+  F A = f_sqr(p.x);
+  F B = f_sqr(p.y);
+  F C = f_sqr(B);
+  F D = f_sub(f_sub(f_sqr(f_add(p.x, B)), A), C);
+  D = f_dbl(D);
+  F E = f_add(f_dbl(A), A);
+  F Fq = f_sqr(E);
+  Jac<F> r;
+  r.z = f_dbl(f_mul(p.y, p.z));
+  r.x = f_sub(Fq, f_dbl(D));
+  F C8 = f_dbl(f_dbl(f_dbl(C)));
+  r.y = f_sub(f_mul(E, f_sub(D, r.x)), C8);
+  return r;
+}
+
+// Jacobian (X, Y, Z) -> extended Jacobian (X, Y, Z^2, Z^3): same X, Y
+template <class F>
+GMSM_HD XYZZ<F> jac_to_xyzz(const Jac<F>& p) {
+  XYZZ<F> r;
+  r.x = p.x;
+  r.y = p.y;
+  r.zz = f_sqr(p.z);
+  r.zzz = f_mul(r.zz, p.z);
+  return r;
+}
+
 // unsafeFromJacExtended g1.go:726-731; infinity (ZZ = ZZZ = 0) maps to (0,0,0)
 template <class F>
 GMSM_HD Jac<F> xyzz_to_jac(const XYZZ<F>& p) {

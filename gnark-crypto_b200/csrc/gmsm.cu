@@ -120,7 +120,8 @@ static int ctx_alloc(gmsm_ctx* c) {
   CK(dmalloc(&c->carries[1], mc2 * xyzz, &acc));
   CK(dmalloc(&c->carry_ids[1], (mc2 + 8) * 4, &acc));
   uint32_t nbmax = std::max(p.nb, p.nb_last);
-  c->seg_L = 32;
+  c->seg_L = 32;  // buckets per reduction segment (GMSM_SEG_L to experiment)
+  if (const char* e = getenv("GMSM_SEG_L")) { int v = atoi(e); if (v >= 2 && v <= 1024) c->seg_L = (uint32_t)v; }
   c->seg_S = (nbmax + c->seg_L - 1) / c->seg_L;
   CK(dmalloc(&c->seg[0], (size_t)p.nwin * c->seg_S * xyzz, &acc));
   CK(dmalloc(&c->seg[1], (size_t)p.nwin * ((c->seg_S + 15) / 16) * xyzz, &acc));

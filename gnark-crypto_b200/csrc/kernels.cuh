@@ -282,8 +282,11 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 //   * bucket begins inside the chunk  -> the thread owns it: buckets[b] = sum
 //   * bucket began in an earlier chunk -> the partial goes to carries[t] (joined by k_carry_level)
 // ------------------------------------------------------------------------------------------
+#ifndef GMSM_ACC_MINBLOCKS_BIG
+#define GMSM_ACC_MINBLOCKS_BIG 1
+#endif
 template <class G>
-__global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : 1)
+__global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : GMSM_ACC_MINBLOCKS_BIG)
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
              XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,
@@ -482,9 +485,13 @@ __global__ void k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  // Horner over the windows, high -> low: acc = 2^c * acc + T_j.  The c doublings run in Jacobian
+  // coordinates (2M + 5S each instead of 6M + 3S); the addition of T_j in extended Jacobian.
   XYZZ<F> acc = load_vec(scratch + (nwin - 1));
   for (int j = nwin - 2; j >= 0; j--) {
-    for (int l = 0; l < c; l++) acc = xyzz_double_cold(acc);
+    Jac<F> dj = xyzz_to_jac(acc);
+    for (int l = 0; l < c; l++) dj = jac_double(dj);
+    acc = jac_to_xyzz(dj);
     XYZZ<F> q = load_vec(scratch + j);
     xyzz_add_cold(acc, q);
   }
