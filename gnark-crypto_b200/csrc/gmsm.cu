@@ -146,6 +146,8 @@ static int ctx_alloc(gmsm_ctx* c) {
   CK(dmalloc(&c->fin_scratch, (size_t)p.nwin * xyzz, &acc));
   c->ws_bytes = acc;
   for (int i = 0; i < 9; i++) CK(cudaEventCreate(&c->ev[i]));
+  CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_split[i], cudaEventDisableTiming));
   return GMSM_OK;
 }
 
@@ -159,6 +161,8 @@ static void ctx_free(gmsm_ctx* c) {
   cudaFree(c->aff_maxlen);
   if (c->aff_maxlen_host) cudaFreeHost(c->aff_maxlen_host);
   for (int i = 0; i < 9; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++) if (c->ev_split[i]) cudaEventDestroy(c->ev_split[i]);
+  if (c->aux) cudaStreamDestroy(c->aux);
 }
 
 extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, int device) {

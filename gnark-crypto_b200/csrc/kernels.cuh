@@ -290,12 +290,20 @@ __global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : GMSM_
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
              XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,
-             uint32_t* __restrict__ carry_ids) {
+             uint32_t* __restrict__ carry_ids, int part, uint32_t split_bucket) {
   using F = typename G::F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
   const uint32_t M = offsets[nb_total];
   const uint64_t start64 = (uint64_t)t * K;
+  // The launch can be split in two parts so that the scatter of the later windows overlaps the first
+  // part: part 1 takes the chunks that end inside the first `split_bucket` buckets (whose entries are
+  // already scattered), part 2 the rest (after the whole scatter); part 0 = everything.
+  if (part != 0) {
+    const uint32_t split = offsets[split_bucket];
+    const bool early = (start64 + K <= split);
+    if ((part == 1) != early) return;
+  }
   if (start64 >= M) {
     carry_ids[t] = ID_NONE;
     return;
