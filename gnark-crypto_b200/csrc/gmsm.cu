@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -309,8 +310,11 @@ static void pipeline_free(Pipeline& P) {
 }
 
 // d_points: device buffer holding (resident) or receiving (h_points != nullptr) the n points
+// c_force = 0: window width from n; otherwise the given width (all shards of a multi-device call must share
+// one window plan).  h_partials != nullptr: stop after the bucket reduction and return the W window partials
+// (host copy) instead of the finalized point.
 static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, const uint64_t* h_scalars, size_t n,
-                        uint64_t* out_jac) {
+                        uint64_t* out_jac, int c_force = 0, void* h_partials = nullptr) {
   CurveInfo ci;
   curve_info(P.curve, &ci);
   const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
@@ -335,7 +339,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     P.scal_cap = n;
   }
   // window width from the TOTAL size (all batches share one bucket array); workspace sized for one batch
-  const int c = choose_c(ci.fr_bits, n);
+  const int c = c_force ? c_force : choose_c(ci.fr_bits, n);
   if (!P.ctx || P.ctx->max_n < nc || P.ctx->max_n > 4 * nc + 1024 || P.ctx->plan.c != c) {
     if (P.ctx) { gmsm_ctx_destroy(P.ctx); P.ctx = nullptr; }
     P.ctx = gmsm_ctx_create((gmsm_curve_t)P.curve, nc, c, P.device);
@@ -349,7 +353,9 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   const GroupVTable* vt = vtable(P.curve);
   const char* hp = reinterpret_cast<const char*>(h_points);
   const char* hs = reinterpret_cast<const char*>(h_scalars);
-  const bool shared_buckets = !P.ctx->affine;   // the batch-affine path keeps per-batch partials instead
+  // the batch-affine path keeps per-batch partials instead (and cannot return per-device partials)
+  const bool shared_buckets = !P.ctx->affine;
+  if (h_partials && !shared_buckets) return set_err(GMSM_EINVAL, "multi-device calls need the default accumulation mode");
   if (shared_buckets && nch > 1 && !P.ctx->buckets2) {
     CK(cudaMalloc(&P.ctx->buckets2, (size_t)P.ctx->plan.nb_total * xb));
   }
@@ -376,6 +382,13 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     P.ctx->last_launches = 0;
     if (int rc = vt->bucket_reduce(P.ctx, P.d_partials, P.comp_st)) return rc;
     launches += P.ctx->last_launches;
+    if (h_partials) {
+      CK(cudaMemcpyAsync(h_partials, P.d_partials, (size_t)P.ctx->plan.nwin * xb, cudaMemcpyDeviceToHost, P.comp_st));
+      CK(cudaStreamSynchronize(P.comp_st));
+      CK(cudaStreamSynchronize(P.copy_st));
+      P.last_launches = launches;
+      return GMSM_OK;
+    }
     if (int rc = vt->finalize(P.ctx, P.d_partials, 1, P.d_out, P.comp_st)) return rc;
   } else {
     if (int rc = vt->finalize(P.ctx, P.d_partials, nch, P.d_out, P.comp_st)) return rc;
@@ -453,25 +466,95 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   if (int rc = check_nb_tasks(nb_tasks)) return rc;
   CurveInfo ci;
   if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
-  int device = 0;
-  if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
-  if (int rc = check_device(device)) return rc;
+  // devices: GMSM_DEVICES="0,1,2,3" shards one call over several GPUs of this process (one host thread per
+  // device, the per-device window partials joined on the first one); default: the single GMSM_DEVICE (0)
+  std::vector<int> devs;
+  if (const char* e = getenv("GMSM_DEVICES")) {
+    for (const char* q = e; *q;) {
+      char* end = nullptr;
+      long v = strtol(q, &end, 10);
+      if (end == q) break;
+      devs.push_back((int)v);
+      q = (*end == ',') ? end + 1 : end;
+    }
+  }
+  if (devs.empty()) {
+    int device = 0;
+    if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
+    devs.push_back(device);
+  }
+  for (int d : devs) if (int rc = check_device(d)) return rc;
   if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
   // per-(curve, device) session: device buffers, streams and the engine context are kept between calls
   // (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
-  struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; };
+  struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; void* d_gather = nullptr; size_t gather_cap = 0; };
   static std::mutex sess_mu;
   static std::map<std::pair<int, int>, Session> sessions;
   std::lock_guard<std::mutex> lk(sess_mu);
-  CK(cudaSetDevice(device));
-  Session& S = sessions[std::make_pair((int)curve, device)];
-  if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
-  if (S.cap < n || S.cap > 4 * n + 1024) {
-    cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
-    CK(cudaMalloc(&S.d_points, n * 8u * ci.coord_words));
-    S.cap = n;
+  const size_t ab = 8u * ci.coord_words;
+  auto prepare = [&](int device, size_t cnt, Session** out) -> int {
+    CK(cudaSetDevice(device));
+    Session& S = sessions[std::make_pair((int)curve, device)];
+    if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
+    if (S.cap < cnt || S.cap > 4 * cnt + 1024) {
+      cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
+      CK(cudaMalloc(&S.d_points, cnt * ab));
+      S.cap = cnt;
+    }
+    *out = &S;
+    return GMSM_OK;
+  };
+  const size_t D = (n >= ((size_t)1 << 16)) ? devs.size() : 1;   // small calls stay on one device
+  if (D == 1) {
+    Session* S = nullptr;
+    if (int rc = prepare(devs[0], n, &S)) return rc;
+    return pipeline_run(S->pipe, S->d_points, points, scalars, n, out_jac);
   }
-  return pipeline_run(S.pipe, S.d_points, points, scalars, n, out_jac);
+  // ---- multi-device: contiguous shards (the reference's recursive halving, multiexp.go:128-140) ----
+  const int c = choose_c(ci.fr_bits, n);
+  const WindowPlan plan = make_plan(ci.fr_bits, c);
+  const size_t xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
+  std::vector<unsigned char> h_part(D * plan.nwin * xb);
+  std::vector<int> rcs(D, GMSM_OK);
+  std::vector<std::string> errs(D);
+  std::vector<Session*> ss(D, nullptr);
+  for (size_t d = 0; d < D; d++) {
+    const size_t lo = n * d / D, hi = n * (d + 1) / D;
+    if (int rc = prepare(devs[d], hi - lo, &ss[d])) return rc;
+  }
+  {
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < D; d++) {
+      th.emplace_back([&, d]() {
+        const size_t lo = n * d / D, hi = n * (d + 1) / D;
+        rcs[d] = pipeline_run(ss[d]->pipe, ss[d]->d_points, points + lo * (ab / 8), scalars + lo * 4, hi - lo, nullptr, c,
+                              h_part.data() + d * plan.nwin * xb);
+        if (rcs[d]) errs[d] = g_err;   // thread-local error text of the worker
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  for (size_t d = 0; d < D; d++)
+    if (rcs[d]) return set_err(rcs[d], "device %d: %s", devs[d], errs[d].c_str());
+  // join on the first device: per-window sum over the D shards, Horner, normalisation
+  Session& S0 = *ss[0];
+  CK(cudaSetDevice(devs[0]));
+  if (S0.gather_cap < h_part.size()) {
+    cudaFree(S0.d_gather); S0.d_gather = nullptr;
+    CK(cudaMalloc(&S0.d_gather, h_part.size()));
+    S0.gather_cap = h_part.size();
+  }
+  CK(cudaMemcpyAsync(S0.d_gather, h_part.data(), h_part.size(), cudaMemcpyHostToDevice, S0.pipe.comp_st));
+  {
+    std::lock_guard<std::mutex> lk2(S0.pipe.ctx->mu);
+    if (int rc = vtable(curve)->finalize(S0.pipe.ctx, S0.d_gather, (int)D, S0.pipe.d_out, S0.pipe.comp_st)) return rc;
+  }
+  CK(cudaMemcpyAsync(out_jac, S0.pipe.d_out, jb, cudaMemcpyDeviceToHost, S0.pipe.comp_st));
+  CK(cudaStreamSynchronize(S0.pipe.comp_st));
+  int launches = 1;
+  for (size_t d = 0; d < D; d++) launches += ss[d]->pipe.last_launches;
+  g_last_oneshot_launches = launches;
+  return GMSM_OK;
 }
 
 extern "C" int gmsm_bn254_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_BN254_G1, p, s, n, t, out); }

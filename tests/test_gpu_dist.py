@@ -54,3 +54,30 @@ def test_sharded_multiexp_nccl(tmp_path):
                        capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK world=%d" % world in r.stdout
+
+
+def test_in_process_multi_device_one_shot(monkeypatch):
+    """GMSM_DEVICES: the one-shot C-ABI call shards over several GPUs of ONE process (host thread per device,
+    partials joined on the first device) -- what a single-process Go caller would use"""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    sys.path.insert(0, ROOT)
+    import gnark_crypto_b200 as pkg
+    from oracle import cref
+    from tests.gpu_common import make_inputs
+
+    ndev = min(torch.cuda.device_count(), 4)
+    for g, n in (("bn254_g1", (1 << 17) + 5), ("bn254_g2", (1 << 16) + 3)):
+        pts, s = make_inputs(g, n, 11)
+        want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=8)
+        A1, J1, A2, J2 = pkg.curve_package("bn254")
+        Aff = A1 if g.endswith("g1") else A2
+        monkeypatch.setenv("GMSM_DEVICES", ",".join(str(d) for d in range(ndev)))
+        got = Aff().MultiExp(pts, s, pkg.MultiExpConfig())
+        assert np.array_equal(got.limbs, want), g
+        monkeypatch.delenv("GMSM_DEVICES")
+        got1 = Aff().MultiExp(pts, s, pkg.MultiExpConfig())
+        assert np.array_equal(got1.limbs, want), g
