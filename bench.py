@@ -323,7 +323,7 @@ def main():
             ds2 = torch.empty(n * 4, dtype=torch.int64, device=d_points.device)
 
             def e2e_step():
-                return sharded.msm_from_host(h_points, h_scal, n, dp2, ds2, chunks=4).cpu().numpy().view(np.uint64)
+                return sharded.msm_from_host_pipelined(hp, hs).cpu().numpy().view(np.uint64)
         for _ in range(2):
             r = e2e_step()
         barrier()
@@ -341,7 +341,7 @@ def main():
         line["e2e"] = {"value": n_total / dt, "unit": "scalar-muls/s", "ms_per_step": dt * 1e3,
                        "h2d_bytes_per_step": n_total * (A + 32), "d2h_bytes_per_step": jac_words * 8 * world,
                        "path": "gmsm_multiexp one-shot (points+scalars H2D every call)" if world == 1 else
-                               "pinned host shards -> chunked H2D overlapped with the bucket pass -> NCCL all-gather of partials -> finalize -> D2H"}
+                               "per rank: gmsm_multiexp_window_sums (pinned host shard, H2D pipelined under the bucket pass) -> NCCL all-gather of W partials -> finalize -> D2H"}
         if world == 1:
             launches_e2e = native.lib().gmsm_last_oneshot_launches()
             line["gpu_launches"] += launches_e2e * args.steps

@@ -461,6 +461,49 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   return pipeline_run(b->pipe, pts, nullptr, scalars, n, out_jac);
 }
 
+// per-(curve, device) session of the host entry points: device buffers, streams and the engine context are kept
+// between calls (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
+struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; void* d_gather = nullptr; size_t gather_cap = 0; };
+static std::mutex g_sess_mu;
+static std::map<std::pair<int, int>, Session> g_sessions;
+
+static int session_prepare(int curve, int device, size_t cnt, Session** out) {
+  CurveInfo ci;
+  curve_info(curve, &ci);
+  CK(cudaSetDevice(device));
+  Session& S = g_sessions[std::make_pair(curve, device)];
+  if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
+  if (S.cap < cnt || S.cap > 4 * cnt + 1024) {
+    cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
+    CK(cudaMalloc(&S.d_points, cnt * 8u * ci.coord_words));
+    S.cap = cnt;
+  }
+  *out = &S;
+  return GMSM_OK;
+}
+
+extern "C" int gmsm_choose_window_bits(gmsm_curve_t curve, size_t n_total) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return 0;
+  return choose_c(ci.fr_bits, n_total);
+}
+
+// one shard of a sharded call, host buffers in, W window partials (host) out: the pipelined engine of
+// gmsm_multiexp without the finalize.  All shards must use the same window width c.
+extern "C" int gmsm_multiexp_window_sums(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n, int c,
+                                         int device, void* out_partials) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  if (c < 2 || c > 24) return set_err(GMSM_EINVAL, "window width c=%d out of range [2,24]", c);
+  if (int rc = check_device(device)) return rc;
+  const WindowPlan plan = make_plan(ci.fr_bits, c);
+  if (n == 0) { memset(out_partials, 0, (size_t)plan.nwin * 16u * ci.coord_words); return GMSM_OK; }
+  std::lock_guard<std::mutex> lk(g_sess_mu);
+  Session* S = nullptr;
+  if (int rc = session_prepare(curve, device, n, &S)) return rc;
+  return pipeline_run(S->pipe, S->d_points, points, scalars, n, nullptr, c, out_partials);
+}
+
 extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
                              uint64_t* out_jac) {
   if (int rc = check_nb_tasks(nb_tasks)) return rc;
@@ -485,25 +528,9 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   }
   for (int d : devs) if (int rc = check_device(d)) return rc;
   if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
-  // per-(curve, device) session: device buffers, streams and the engine context are kept between calls
-  // (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
-  struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; void* d_gather = nullptr; size_t gather_cap = 0; };
-  static std::mutex sess_mu;
-  static std::map<std::pair<int, int>, Session> sessions;
-  std::lock_guard<std::mutex> lk(sess_mu);
+  std::lock_guard<std::mutex> lk(g_sess_mu);
   const size_t ab = 8u * ci.coord_words;
-  auto prepare = [&](int device, size_t cnt, Session** out) -> int {
-    CK(cudaSetDevice(device));
-    Session& S = sessions[std::make_pair((int)curve, device)];
-    if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
-    if (S.cap < cnt || S.cap > 4 * cnt + 1024) {
-      cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
-      CK(cudaMalloc(&S.d_points, cnt * ab));
-      S.cap = cnt;
-    }
-    *out = &S;
-    return GMSM_OK;
-  };
+  auto prepare = [&](int device, size_t cnt, Session** out) -> int { return session_prepare(curve, device, cnt, out); };
   const size_t D = (n >= ((size_t)1 << 16)) ? devs.size() : 1;   // small calls stay on one device
   if (D == 1) {
     Session* S = nullptr;

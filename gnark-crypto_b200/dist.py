@@ -70,6 +70,27 @@ class ShardedMultiExp:
         allp = gather_partials(partials, self.world, self.group)
         return self.engine.finalize(allp, self.world * chunks)
 
+    def msm_from_host_pipelined(self, h_points_np, h_scalars_np):
+        """End-to-end sharded MSM through the C ABI's pipelined host entry point (geometric batches into one shared
+        bucket array, H2D under compute): every rank gets its W window partials back, the ranks all-gather them
+        over NCCL and finalize.  h_points_np / h_scalars_np: this rank's (pinned) numpy shards, Go layout."""
+        import numpy as np
+
+        from . import _native
+        from .multiexp import MultiExpError
+
+        torch = self.engine.torch
+        eng = self.engine
+        n_local = h_scalars_np.size // 4
+        part = np.empty(eng.partials_bytes // 8, dtype=np.uint64)
+        rc = _native.lib().gmsm_multiexp_window_sums(eng.cid, h_points_np.ctypes.data, h_scalars_np.ctypes.data, n_local, eng.c,
+                                                     eng.device, part.ctypes.data)
+        if rc != 0:
+            raise MultiExpError(_native.last_error())
+        local = torch.from_numpy(part.view(np.int64)).to(torch.device("cuda", eng.device))
+        allp = gather_partials(local, self.world, self.group)
+        return eng.finalize(allp, self.world)
+
     def msm(self, d_points_shard, d_scalars_shard, n_local: int):
         partials = self.engine.window_sums(d_points_shard, d_scalars_shard, n_local)
         allp = gather_partials(partials, self.world, self.group)

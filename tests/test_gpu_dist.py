@@ -32,6 +32,16 @@ eng = pkg.Engine(g, hi - lo, c=13, device=lr)
 sh = distmod.ShardedMultiExp(eng)
 jac = sh.msm(eng.to_device(pts[lo:hi]), eng.to_device(s[lo:hi]), hi - lo).cpu().numpy().view(np.uint64)
 assert np.array_equal(jac[:8], want), "rank %d: sharded result differs from oracle" % rank
+# host-buffer variant through the C ABI's pipelined shard entry point (gmsm_multiexp_window_sums)
+eng2 = pkg.Engine(g, hi - lo, c=0, device=lr)
+sh2 = distmod.ShardedMultiExp(eng2)
+jac2 = sh2.msm_from_host_pipelined(np.ascontiguousarray(pts[lo:hi]), np.ascontiguousarray(s[lo:hi])).cpu().numpy().view(np.uint64)
+assert np.array_equal(jac2[:8], want), "rank %d: pipelined host-shard result differs from oracle" % rank
+jac3 = sh.msm_from_host(torch.from_numpy(pts[lo:hi].view(np.int64).reshape(-1).copy()).pin_memory(),
+                        torch.from_numpy(s[lo:hi].view(np.int64).reshape(-1).copy()).pin_memory(), hi - lo,
+                        torch.empty((hi - lo) * 8, dtype=torch.int64, device="cuda"),
+                        torch.empty((hi - lo) * 4, dtype=torch.int64, device="cuda"), chunks=3).cpu().numpy().view(np.uint64)
+assert np.array_equal(jac3[:8], want), "rank %d: chunked torch-copy result differs from oracle" % rank
 dist.barrier()
 if rank == 0:
     print("DIST_OK world=%d" % world)
