@@ -288,3 +288,33 @@ def test_kzg_commit_over_generated_srs_and_dump_roundtrip(tmp_path):
     with pytest.raises(kzg.ErrInvalidPolynomialSize):
         kzg.Commit(np.zeros((0, 4), dtype=np.uint64), pk)
     pk.close()
+
+
+def test_concurrent_callers_are_safe():
+    """BenchmarkManyMultiExpG1Reference (multiexp_test.go:385-415) launches 3 MSMs from 3 goroutines; the C ABI
+    must be callable from several OS threads at once (ctypes drops the GIL during the call)"""
+    import threading
+
+    pkg = _pkg()
+    cases = []
+    for i, (g, n) in enumerate([("bn254_g1", 30000), ("bn254_g1", 70000), ("bn254_g2", 9000), ("bls12381_g1", 20000)]):
+        pts, s = make_inputs(g, n, 100 + i)
+        want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+        cases.append((g, pts, s, want))
+    results = [None] * (3 * len(cases))
+
+    def work(k):
+        g, pts, s, want = cases[k % len(cases)]
+        A1, J1, A2, J2 = pkg.curve_package(g.split("_")[0])
+        Aff = A1 if g.endswith("g1") else A2
+        ok = True
+        for _ in range(3):
+            ok = ok and np.array_equal(Aff().MultiExp(pts, s, pkg.MultiExpConfig()).limbs, want)
+        results[k] = ok
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(results))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(results), results

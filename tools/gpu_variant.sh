@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dist.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -4
-for DEVS in 0 0,1 0,1,2,3; do
-  GMSM_DEVICES=$DEVS timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/v_md.json 2>gpurun_out/v.err
-  python -c "
-import json; d=json.load(open('gpurun_out/v_md.json')); print('GMSM_DEVICES=$DEVS dev ms', round(d['ms_per_step'],2), 'one-shot e2e ms', round(d['e2e']['ms_per_step'],2), 'M/s', round(d['e2e']['value']/1e6,1))" || tail -3 gpurun_out/v.err
-done
+timeout 900 python -m pytest tests/test_gpu_dist.py tests/test_cpp_mirror.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -4
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/scale_n2.json 2> gpurun_out/scale_n2.err
+echo "N=2 rc=$?"; python -c "
+import json
+d=json.loads(open('gpurun_out/scale_n2.json').read().strip().splitlines()[-1]); print('N=2 value', round(d['value']/1e6,1), 'M/s ms', round(d['ms_per_step'],2), 'e2e ms', round(d['e2e']['ms_per_step'],2), 'e2e value', round(d['e2e']['value']/1e6,1))"; grep -iE "error" gpurun_out/scale_n2.err | tail -3
