@@ -21,7 +21,8 @@ SYMBOLS = [
     "gmsm_multiexp", "gmsm_choose_window_bits", "gmsm_multiexp_window_sums", "gmsm_last_oneshot_launches", "gmsm_bases_upload", "gmsm_bases_multiexp", "gmsm_bases_free",
     "gmsm_ctx_create", "gmsm_ctx_destroy", "gmsm_ctx_window_bits", "gmsm_ctx_num_windows", "gmsm_ctx_workspace_bytes",
     "gmsm_ctx_last_launches", "gmsm_ctx_msm_device", "gmsm_ctx_window_sums_device", "gmsm_ctx_finalize_device",
-    "gmsm_ctx_set_profiling", "gmsm_ctx_last_stage_ms", "gmsm_generate_multiples_device", "gmsm_batch_scalar_mul", "gmsm_test_op", "gmsm_test_digits",
+    "gmsm_ctx_set_profiling", "gmsm_ctx_last_stage_ms", "gmsm_generate_multiples_device", "gmsm_batch_scalar_mul", "gmsm_fft_domain_create", "gmsm_fft_domain_free", "gmsm_fft_domain_cardinality",
+    "gmsm_fft_domain_constants", "gmsm_fft", "gmsm_fft_inverse", "gmsm_fft_device", "gmsm_fft_bit_reverse_device", "gmsm_test_op", "gmsm_test_digits",
 ]
 
 _lib = None
@@ -73,6 +74,17 @@ def lib() -> ctypes.CDLL:
     L.gmsm_ctx_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.gmsm_generate_multiples_device.argtypes = [i32, vp, ctypes.c_uint64, sz, vp, vp]
     L.gmsm_batch_scalar_mul.argtypes = [i32, vp, vp, sz, vp]
+    L.gmsm_fft_domain_create.restype = vp
+    L.gmsm_fft_domain_create.argtypes = [i32, ctypes.c_uint64, vp, i32]
+    L.gmsm_fft_domain_free.argtypes = [vp]
+    L.gmsm_fft_domain_free.restype = None
+    L.gmsm_fft_domain_cardinality.argtypes = [vp]
+    L.gmsm_fft_domain_cardinality.restype = ctypes.c_uint64
+    L.gmsm_fft_domain_constants.argtypes = [vp, vp]
+    L.gmsm_fft.argtypes = [vp, vp, sz, i32, i32]
+    L.gmsm_fft_inverse.argtypes = [vp, vp, sz, i32, i32]
+    L.gmsm_fft_device.argtypes = [vp, vp, sz, i32, i32, i32, vp]
+    L.gmsm_fft_bit_reverse_device.argtypes = [vp, vp, sz, vp]
     L.gmsm_test_op.argtypes = [i32, i32, vp, vp, vp, sz]
     L.gmsm_test_digits.argtypes = [i32, i32, vp, sz, vp]
     _lib = L

@@ -131,6 +131,26 @@ int gmsm_generate_multiples_device(gmsm_curve_t curve, const uint64_t* base_affi
 int gmsm_batch_scalar_mul(gmsm_curve_t curve, const uint64_t* base_affine, const uint64_t* scalars, size_t n,
                           uint64_t* out_points);
 
+/* ---- next-row N3: Fr FFT behind gnark-crypto's fft.Domain (ecc/bn254/fr/fft/domain.go:24-110, fft.go:31-190,
+ * bitreverse.go:17-42; ecc/bls12-381/fr/fft identical).  `a` is the []fr.Element image (n x 4 u64, Montgomery),
+ * transformed in place; len(a) must equal the domain cardinality.  decimation: GMSM_DIT = 0 (input bit-reversed,
+ * output natural), GMSM_DIF = 1 (input natural, output bit-reversed) -- fft.Decimation, fft.go:18-23.  coset != 0
+ * = fft.OnCoset().  FFTInverse includes the scaling by CardinalityInv. ---- */
+typedef struct gmsm_fft_domain gmsm_fft_domain_t;
+enum { GMSM_FR_BN254 = 0, GMSM_FR_BLS12381 = 1 };
+enum { GMSM_DIT = 0, GMSM_DIF = 1 };
+/* NewDomain(m) / NewDomain(m, WithShift(shift)): cardinality = next power of two >= m; shift = NULL selects
+ * GeneratorFullMultiplicativeGroup() (5 / 7), otherwise 4 u64 Montgomery limbs */
+gmsm_fft_domain_t* gmsm_fft_domain_create(int fr_field, uint64_t m, const uint64_t* shift, int device);
+void gmsm_fft_domain_free(gmsm_fft_domain_t* domain);
+uint64_t gmsm_fft_domain_cardinality(const gmsm_fft_domain_t* domain);
+/* Generator, GeneratorInv, CardinalityInv, FrMultiplicativeGen, FrMultiplicativeGenInv (5 x 4 u64, Montgomery) */
+int gmsm_fft_domain_constants(const gmsm_fft_domain_t* domain, uint64_t out[20]);
+int gmsm_fft(gmsm_fft_domain_t* domain, uint64_t* a, size_t n, int decimation, int coset);           /* host buffer */
+int gmsm_fft_inverse(gmsm_fft_domain_t* domain, uint64_t* a, size_t n, int decimation, int coset);   /* host buffer */
+int gmsm_fft_device(gmsm_fft_domain_t* domain, void* d_a, size_t n, int inverse, int decimation, int coset, void* stream);
+int gmsm_fft_bit_reverse_device(gmsm_fft_domain_t* domain, void* d_a, size_t n, void* stream);        /* fft.BitReverse */
+
 /* ---- 5. test hooks: element-wise device functions, used by tests/ to check the sm_100a field and
  * point arithmetic against the oracle.  a, b, out are HOST arrays of n elements each. ---- */
 enum {

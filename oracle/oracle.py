@@ -709,3 +709,111 @@ def consecutive_multiples(G: Group, n: int, start_k: int = 1, base=None):
         out.append(p)
         p = G.aff_add(p, base)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Next-row N3: Fr FFT (ecc/bn254/fr/fft/domain.go:67-110, fft.go:31-190, bitreverse.go:17-42;
+# ecc/bls12-381/fr/fft/ identical with its own constants).  Plain integers mod r.
+# --------------------------------------------------------------------------------------
+
+# fr.Generator (ecc/bn254/fr/generator.go:18-36, ecc/bls12-381/fr/generator.go) and
+# GeneratorFullMultiplicativeGroup (fft/domain.go:55-63)
+FFT_PARAMS = {
+    "bn254_fr": dict(root=19103219067921713944291392827692070036145651957329286315305642004821462161904, max_order=28, mult_gen=5),
+    "bls12381_fr": dict(root=10238227357739495823651030575849232062558860180284477541189508159991286009131, max_order=32, mult_gen=7),
+}
+DIT, DIF = 0, 1  # fft.Decimation (fft.go:18-23)
+
+
+def bit_reverse(v):
+    """BitReverse (bitreverse.go:17-42): in-place bit-reversal permutation, returns the list"""
+    n = len(v)
+    assert n & (n - 1) == 0
+    lg = n.bit_length() - 1
+    for i in range(n):
+        r = int(bin(i)[2:].zfill(lg)[::-1], 2) if lg else 0
+        if r > i:
+            v[i], v[r] = v[r], v[i]
+    return v
+
+
+class FFTDomain:
+    """fft.Domain / NewDomain (domain.go:24-110)"""
+
+    def __init__(self, frname: str, m: int, shift: int = None):
+        f = FIELDS[frname]
+        P = FFT_PARAMS[frname]
+        self.q = f.q
+        x = 1
+        while x < m:
+            x <<= 1
+        self.cardinality = x
+        logx = x.bit_length() - 1
+        if logx > P["max_order"]:
+            raise ValueError("m (%d) is too big: the required root of unity does not exist" % m)
+        self.generator = pow(P["root"], 1 << (P["max_order"] - logx), self.q)
+        self.generator_inv = pow(self.generator, -1, self.q)
+        self.cardinality_inv = pow(x, -1, self.q)
+        self.shift = P["mult_gen"] if shift is None else shift % self.q
+        self.shift_inv = pow(self.shift, -1, self.q)
+
+    def _dif(self, a, w):
+        # difFFT (fft.go:195-260): natural order in, bit-reversed order out
+        q = self.q
+        n = len(a)
+        m = n >> 1
+        while m >= 1:
+            wm = pow(w, n // (2 * m), q)
+            for start in range(0, n, 2 * m):
+                t = 1
+                for j in range(m):
+                    x, y = a[start + j], a[start + j + m]
+                    a[start + j] = (x + y) % q
+                    a[start + j + m] = (x - y) * t % q
+                    t = t * wm % q
+            m >>= 1
+        return a
+
+    def _dit(self, a, w):
+        # ditFFT (fft.go:262+): bit-reversed order in, natural order out
+        q = self.q
+        n = len(a)
+        m = 1
+        while m < n:
+            wm = pow(w, n // (2 * m), q)
+            for start in range(0, n, 2 * m):
+                t = 1
+                for j in range(m):
+                    x, y = a[start + j], a[start + j + m] * t % q
+                    a[start + j] = (x + y) % q
+                    a[start + j + m] = (x - y) % q
+                    t = t * wm % q
+            m <<= 1
+        return a
+
+    def _rev(self, i):
+        lg = self.cardinality.bit_length() - 1
+        return int(bin(i)[2:].zfill(lg)[::-1], 2) if lg else 0
+
+    def fft(self, a, decimation, coset=False):
+        """Domain.FFT (fft.go:31-110)"""
+        a = [v % self.q for v in a]
+        assert len(a) == self.cardinality
+        if coset:
+            for i in range(len(a)):
+                e = self._rev(i) if decimation == DIT else i
+                a[i] = a[i] * pow(self.shift, e, self.q) % self.q
+        return self._dif(a, self.generator) if decimation == DIF else self._dit(a, self.generator)
+
+    def fft_inverse(self, a, decimation, coset=False):
+        """Domain.FFTInverse (fft.go:117-190)"""
+        a = [v % self.q for v in a]
+        assert len(a) == self.cardinality
+        a = self._dif(a, self.generator_inv) if decimation == DIF else self._dit(a, self.generator_inv)
+        for i in range(len(a)):
+            s = self.cardinality_inv
+            if coset:
+                e = i if decimation == DIT else self._rev(i)
+                s = s * pow(self.shift_inv, e, self.q) % self.q
+            a[i] = a[i] * s % self.q
+        return a
