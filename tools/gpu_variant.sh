@@ -1,7 +1,22 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dist.py tests/test_cpp_mirror.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -4
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/scale_n2.json 2> gpurun_out/scale_n2.err
-echo "N=2 rc=$?"; python -c "
-import json
-d=json.loads(open('gpurun_out/scale_n2.json').read().strip().splitlines()[-1]); print('N=2 value', round(d['value']/1e6,1), 'M/s ms', round(d['ms_per_step'],2), 'e2e ms', round(d['e2e']['ms_per_step'],2), 'e2e value', round(d['e2e']['value']/1e6,1))"; grep -iE "error" gpurun_out/scale_n2.err | tail -3
+timeout 900 python -m pytest tests/test_gpu_fft.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -8
+timeout 300 python - <<'PY'
+import importlib, time, numpy as np, torch, sys
+sys.path.insert(0,'.')
+import gnark_crypto_b200
+fft = importlib.import_module("gnark-crypto_b200.fft")
+for logn in (20, 24):
+    n = 1 << logn
+    d = fft.NewDomain("bn254", n)
+    a = torch.randint(0, 2**59, (n*4,), dtype=torch.int64, device="cuda")
+    for _ in range(3): d.fft_device(a, False, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): d.fft_device(a, False, 1)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/5
+    print("bn254 fr FFT DIF n=2^%d: %.3f ms  (%.1f GB/s algorithmic at %d passes of 64 B/elt)" % (logn, ms, (logn-10+1)*n*64/ms/1e6, logn-10+1))
+    d.close()
+PY
