@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--curve", default="bn254_g1", choices=list(CURVE_BITS))
     ap.add_argument("--logn", type=int, default=24, help="log2 of points PER GPU")
+    ap.add_argument("--total-logn", type=int, default=0,
+                    help="strong scaling: log2 of the TOTAL number of points, sharded over the N ranks (e.g. 26 for BASELINE "
+                         "configs[4]); default 0 = weak scaling with 2^logn points per GPU")
     ap.add_argument("--c", type=int, default=0, help="window width (0 = engine model)")
     ap.add_argument("--sample-logn", type=int, default=0, help="cpu baseline sample size (log2)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,7 +207,13 @@ def main():
 
     g = args.curve
     bits = CURVE_BITS[g]
-    n = 1 << args.logn                      # per GPU (weak scaling)
+    scaling = "weak"
+    if args.total_logn:
+        scaling = "strong"
+        if (1 << args.total_logn) % world:
+            raise SystemExit("--total-logn: 2^%d is not divisible by %d ranks" % (args.total_logn, world))
+        args.logn = args.total_logn - (world.bit_length() - 1)
+    n = 1 << args.logn                      # per GPU
     n_total = n * world
     lo, hi = distmod.shard_range(n_total, rank, world)
     assert hi - lo == n
@@ -289,7 +298,7 @@ def main():
     line = {
         "metric": "bn254 G1 MultiExp scalar-muls/s" if g == "bn254_g1" else g + " MultiExp scalar-muls/s",
         "value": value, "unit": "scalar-muls/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": "%s MultiExp n=2^%d per GPU%s, random scalars, on-curve bases [i]B" % (
             g, args.logn, " (BASELINE configs[1])" if (g == "bn254_g1" and args.logn == 24) else ""),
