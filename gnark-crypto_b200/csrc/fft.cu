@@ -177,6 +177,8 @@ struct FrConsts {
 };
 const FrConsts FR_BN254 = {"19103219067921713944291392827692070036145651957329286315305642004821462161904", 28, 5};
 const FrConsts FR_BLS12381 = {"10238227357739495823651030575849232062558860180284477541189508159991286009131", 32, 7};
+// ecc/bls12-377/fr/generator.go:23-24, fr/fft/domain.go:59
+const FrConsts FR_BLS12377 = {"8065159656716812877374967518403273466521432693661810619979959746626482506078", 47, 22};
 
 }  // namespace
 
@@ -258,13 +260,13 @@ static int run_fft(gmsm_fft_domain* d, void* d_a, int inverse, int decimation, i
 }
 
 extern "C" gmsm_fft_domain_t* gmsm_fft_domain_create(int fr_field, uint64_t m, const uint64_t* shift, int device) {
-  if (fr_field != 0 && fr_field != 1) { set_err(GMSM_EINVAL, "unknown scalar field %d", fr_field); return nullptr; }
+  if (fr_field < 0 || fr_field > 2) { set_err(GMSM_EINVAL, "unknown scalar field %d", fr_field); return nullptr; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { set_err(GMSM_ENODEV, "no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
   if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range", device); return nullptr; }
   cudaSetDevice(device);
-  const FrConsts& fc = fr_field == 0 ? FR_BN254 : FR_BLS12381;
+  const FrConsts& fc = fr_field == 0 ? FR_BN254 : (fr_field == 1 ? FR_BLS12381 : FR_BLS12377);
   uint64_t x = 1;
   int logn = 0;
   while (x < m) { x <<= 1; logn++; }   // ecc.NextPowerOfTwo(m)
@@ -274,7 +276,8 @@ extern "C" gmsm_fft_domain_t* gmsm_fft_domain_create(int fr_field, uint64_t m, c
   }
   gmsm_fft_domain* d = new gmsm_fft_domain();
   d->field = fr_field; d->device = device; d->n = x; d->logn = logn;
-  int rc = fr_field == 0 ? domain_build<bn254_fr>(d, fc, shift) : domain_build<bls12381_fr>(d, fc, shift);
+  int rc = fr_field == 0 ? domain_build<bn254_fr>(d, fc, shift)
+                         : (fr_field == 1 ? domain_build<bls12381_fr>(d, fc, shift) : domain_build<bls12377_fr>(d, fc, shift));
   if (rc == GMSM_OK && cudaMalloc(&d->d_buf, x * 32) != cudaSuccess) rc = set_err(GMSM_ENOMEM, "cudaMalloc(%llu) failed", (unsigned long long)(x * 32));
   if (rc != GMSM_OK) { cudaFree(d->d_tw); cudaFree(d->d_tw_inv); cudaFree(d->d_pw); cudaFree(d->d_buf); delete d; return nullptr; }
   return d;
@@ -301,8 +304,9 @@ extern "C" int gmsm_fft_device(gmsm_fft_domain_t* d, void* d_a, size_t n, int in
   if (decimation != 0 && decimation != 1) return set_err(GMSM_EINVAL, "not implemented");  // fft.go:108
   std::lock_guard<std::mutex> lk(d->mu);
   CK(cudaSetDevice(d->device));
-  return d->field == 0 ? run_fft<bn254_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream)
-                       : run_fft<bls12381_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
+  if (d->field == 0) return run_fft<bn254_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
+  if (d->field == 1) return run_fft<bls12381_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
+  return run_fft<bls12377_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
 }
 
 static int fft_host(gmsm_fft_domain_t* d, uint64_t* a, size_t n, int inverse, int decimation, int coset) {
@@ -328,7 +332,8 @@ extern "C" int gmsm_fft_bit_reverse_device(gmsm_fft_domain_t* d, void* d_a, size
   CK(cudaSetDevice(d->device));
   unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148u * 32u);
   if (d->field == 0) k_fft_bit_reverse<bn254_fr><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Fp<bn254_fr>*>(d_a), n, d->logn);
-  else k_fft_bit_reverse<bls12381_fr><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Fp<bls12381_fr>*>(d_a), n, d->logn);
+  else if (d->field == 1) k_fft_bit_reverse<bls12381_fr><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Fp<bls12381_fr>*>(d_a), n, d->logn);
+  else k_fft_bit_reverse<bls12377_fr><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Fp<bls12377_fr>*>(d_a), n, d->logn);
   CK(cudaGetLastError());
   return GMSM_OK;
 }

@@ -29,6 +29,8 @@ using bn254_g1 = GroupT<0, bn254_fp, bn254_fr, false>;
 using bn254_g2 = GroupT<1, bn254_fp, bn254_fr, true>;
 using bls12381_g1 = GroupT<2, bls12381_fp, bls12381_fr, false>;
 using bls12381_g2 = GroupT<3, bls12381_fp, bls12381_fr, true>;
+// next-row N4 (pure parametrisation): bls12-377 G1, ecc/bls12-377/g1.go, fr 253 bits
+using bls12377_g1 = GroupT<4, bls12377_fp, bls12377_fr, false>;
 
 // word (u32) counts
 template <class G> constexpr int coord_words() { return G::F::N; }

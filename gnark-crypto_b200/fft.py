@@ -11,7 +11,7 @@ from . import _native
 from .multiexp import MultiExpError
 
 DIT, DIF = 0, 1  # fft.Decimation
-_FIELDS = {"bn254": 0, "bls12381": 1}
+_FIELDS = {"bn254": 0, "bls12381": 1, "bls12377": 2}
 
 
 class Domain:

@@ -39,7 +39,8 @@ typedef enum {
   GMSM_BN254_G1 = 0,
   GMSM_BN254_G2 = 1,
   GMSM_BLS12381_G1 = 2,
-  GMSM_BLS12381_G2 = 3
+  GMSM_BLS12381_G2 = 3,
+  GMSM_BLS12377_G1 = 4   /* next-row N4: ecc/bls12-377 (G1 only; its G2 tower has u^2 = -5) */
 } gmsm_curve_t;
 
 enum {
@@ -70,6 +71,8 @@ int gmsm_bls12381_g1_multiexp(const uint64_t* points, const uint64_t* scalars, s
                               uint64_t out_jac[18]);
 int gmsm_bls12381_g2_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
                               uint64_t out_jac[36]);
+int gmsm_bls12377_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[18]);   /* ecc/bls12-377/multiexp.go:32 */
 int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n,
                   int nb_tasks, uint64_t* out_jac);
 /* sharded calls with one process per GPU: every process runs its shard through the pipelined engine and gets the W
@@ -137,7 +140,7 @@ int gmsm_batch_scalar_mul(gmsm_curve_t curve, const uint64_t* base_affine, const
  * output natural), GMSM_DIF = 1 (input natural, output bit-reversed) -- fft.Decimation, fft.go:18-23.  coset != 0
  * = fft.OnCoset().  FFTInverse includes the scaling by CardinalityInv. ---- */
 typedef struct gmsm_fft_domain gmsm_fft_domain_t;
-enum { GMSM_FR_BN254 = 0, GMSM_FR_BLS12381 = 1 };
+enum { GMSM_FR_BN254 = 0, GMSM_FR_BLS12381 = 1, GMSM_FR_BLS12377 = 2 };
 enum { GMSM_DIT = 0, GMSM_DIF = 1 };
 /* NewDomain(m) / NewDomain(m, WithShift(shift)): cardinality = next power of two >= m; shift = NULL selects
  * GeneratorFullMultiplicativeGroup() (5 / 7), otherwise 4 u64 Montgomery limbs */

@@ -145,6 +145,21 @@ FIELDS = {
             rsquare=[14526898881837571181, 3129137299524312099, 419701826671360399, 524908885293268753],
         ),
     ),
+    # next-row N4: ecc/bls12-377/fp/element.go:28-31,75,928-935 ; fr/element.go:28-31,71,773-778
+    "bls12377_fp": Field(
+        "bls12377_fp",
+        0x1AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001,
+        6,
+        dict(qinvneg=9586122913090633727,
+             rsquare=[13224372171368877346, 227991066186625457, 2496666625421784173, 13825906835078366124, 9475172226622360569,
+                      30958721782860680]),
+    ),
+    "bls12377_fr": Field(
+        "bls12377_fr",
+        0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001,
+        4,
+        dict(qinvneg=725501752471715839, rsquare=[2726216793283724667, 14712177743343147295, 12091039717619697043, 81024008013859129]),
+    ),
 }
 
 
@@ -530,6 +545,17 @@ def _mk_groups():
             ),
         ),
     )
+    # next-row N4: ecc/bls12-377/bls12-377.go:9,102,107-108 : Y^2 = X^3 + 1
+    g["bls12377_g1"] = Group(
+        "bls12377_g1",
+        FpOps(FIELDS["bls12377_fp"]),
+        FIELDS["bls12377_fr"],
+        1,
+        (
+            81937999373150964239938255573465948239988671502647976594219695644855304257327692006745978603320413799295628339695,
+            241266749859715473739788878240585681733927191168601896383759122102112907357779751001206799952863815012735208165030,
+        ),
+    )
     return g
 
 
@@ -721,6 +747,8 @@ def consecutive_multiples(G: Group, n: int, start_k: int = 1, base=None):
 FFT_PARAMS = {
     "bn254_fr": dict(root=19103219067921713944291392827692070036145651957329286315305642004821462161904, max_order=28, mult_gen=5),
     "bls12381_fr": dict(root=10238227357739495823651030575849232062558860180284477541189508159991286009131, max_order=32, mult_gen=7),
+    # ecc/bls12-377/fr/generator.go:23-24, fr/fft/domain.go:59
+    "bls12377_fr": dict(root=8065159656716812877374967518403273466521432693661810619979959746626482506078, max_order=47, mult_gen=22),
 }
 DIT, DIF = 0, 1  # fft.Decimation (fft.go:18-23)
 

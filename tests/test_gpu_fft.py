@@ -10,7 +10,7 @@ import pytest
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-FR = {"bn254": "bn254_fr", "bls12381": "bls12381_fr"}
+FR = {"bn254": "bn254_fr", "bls12381": "bls12381_fr", "bls12377": "bls12377_fr"}
 
 
 def _fft():
@@ -27,7 +27,7 @@ def _dec(f, arr):
     return [f.from_mont(O.Field.from_limbs([int(x) for x in r])) for r in arr]
 
 
-@pytest.mark.parametrize("curve", ["bn254", "bls12381"])
+@pytest.mark.parametrize("curve", ["bn254", "bls12381", "bls12377"])
 @pytest.mark.parametrize("logn", [0, 1, 2, 5, 10, 11, 13])
 def test_fft_matches_oracle(curve, logn):
     fft = _fft()

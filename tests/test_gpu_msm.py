@@ -38,7 +38,8 @@ def _engine_msm(g, pts, s, c):
         eng.close()
 
 
-@pytest.mark.parametrize("g,n", [("bn254_g1", 2000), ("bls12381_g1", 1200), ("bn254_g2", 1000), ("bls12381_g2", 500)])
+@pytest.mark.parametrize("g,n", [("bn254_g1", 2000), ("bls12381_g1", 1200), ("bn254_g2", 1000), ("bls12381_g2", 500),
+                                 ("bls12377_g1", 1000)])
 def test_all_window_sizes_agree_with_oracle(g, n, accumulate_mode):
     """every c the reference implements (2..16) plus the wider windows the GPU model may pick"""
     pts, s = make_inputs(g, n, 1234)
@@ -80,7 +81,7 @@ def test_config1_n65536_bn254_g1(accumulate_mode):
     rb.close()
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bn254_g2", "bls12381_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12377_g1"])
 def test_infinity_zero_and_empty(g, accumulate_mode):
     pkg = _pkg()
     A1, J1, A2, J2 = pkg.curve_package(g.split("_")[0])
@@ -135,7 +136,7 @@ def test_skewed_scalar_distributions(kind, accumulate_mode):
         assert np.array_equal(jac[:8], want), (kind, c)
 
 
-@pytest.mark.parametrize("g,n", [("bn254_g1", 1 << 20), ("bls12381_g1", 1 << 18), ("bn254_g2", 1 << 17)])
+@pytest.mark.parametrize("g,n", [("bn254_g1", 1 << 20), ("bls12381_g1", 1 << 18), ("bn254_g2", 1 << 17), ("bls12377_g1", 1 << 18)])
 def test_large_closed_form_on_device_bases(g, n, accumulate_mode):
     """size-independent property at large n: bases [i+1]B generated on the device, result must equal
     [sum (i+1) s_i mod r] B (the KZG TestCommit identity, kzg_test.go:209-239); also pins the device

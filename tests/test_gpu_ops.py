@@ -33,7 +33,7 @@ def test_point_ops_device(g):
     opcases.check_point_ops(O.GROUPS[g], _runner(g))
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1"])
 def test_field_mul_bulk_random(g):
     """20k random products per base field against the C oracle (the Python one is pinned to it)"""
     G = O.GROUPS[g]
@@ -46,12 +46,12 @@ def test_field_mul_bulk_random(g):
     top = (1 << (f.bits - 64 * (L - 1) - 1)) - 1  # < q for sure
     a[:, -1] &= np.uint64(top)
     b[:, -1] &= np.uint64(top)
-    want = cref.field_op(0 if g == "bn254_g1" else 2, 0, a, b)
+    want = cref.field_op({"bn254_g1": 0, "bls12381_g1": 2, "bls12377_g1": 4}[g], 0, a, b)
     got = _runner(g)(opcases.OPS["FMUL"], opcases.u32(a), opcases.u32(b), 2 * L)
     assert np.array_equal(got.view(np.uint64), want)
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1"])
 @pytest.mark.parametrize("c", [2, 3, 5, 8, 11, 13, 15, 16, 17, 20, 23, 24])
 def test_digits_match_partition_scalars(g, c):
     from importlib import import_module

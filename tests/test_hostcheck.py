@@ -25,7 +25,7 @@ def hc():
 
 def _runner(hc, g):
     cid = list(O.GROUPS).index(g)
-    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2"]
+    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1"]
 
     def run(op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)
@@ -53,7 +53,7 @@ def test_point_ops_host(hc, g):
 
 def test_window_plan(hc):
     buf = (ctypes.c_int * 6)()
-    for bits in (254, 255):
+    for bits in (253, 254, 255):
         for c in range(2, 25):
             hc.hostcheck_plan(bits, c, buf)
             W = O.compute_nb_chunks(bits, c)

@@ -113,7 +113,7 @@ def test_bls12381_g2_hash_vector_known_answer():
 # ---------------------------------------------------------------------------------------
 
 
-@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr"])
+@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr", "bls12377_fr"])
 @pytest.mark.parametrize("c", [2, 3, 5, 8, 11, 13, 14, 15, 16, 20, 23])
 def test_partition_scalars_reconstructs(frname, c):
     fr = O.FIELDS[frname]
@@ -164,7 +164,7 @@ def _inputs(G, n, seed, n_inf=0):
     return pts, ks
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bn254_g2"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bn254_g2", "bls12377_g1"])
 def test_msm_all_c_agree(g):
     # multiexp_test.go:95-126 : 73 points, 4 random ones set to infinity, every c agrees
     G = O.GROUPS[g]

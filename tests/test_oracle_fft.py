@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle as O
 
 
-@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr"])
+@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr", "bls12377_fr"])
 def test_domain_constants(frname):
     q = O.FIELDS[frname].q
     for lg in (1, 4, 10, 20):
@@ -17,13 +17,13 @@ def test_domain_constants(frname):
         assert pow(d.generator, 1 << lg, q) == 1 and pow(d.generator, 1 << (lg - 1), q) == q - 1
         assert d.generator * d.generator_inv % q == 1 and d.cardinality * d.cardinality_inv % q == 1
     with pytest.raises(ValueError):
-        O.FFTDomain(frname, 1 << 40)
+        O.FFTDomain(frname, 1 << 48)
     # maximal 2-adic order really is max_order: root^(2^(max-1)) = -1
     P = O.FFT_PARAMS[frname]
     assert pow(P["root"], 1 << (P["max_order"] - 1), q) == q - 1
 
 
-@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr"])
+@pytest.mark.parametrize("frname", ["bn254_fr", "bls12381_fr", "bls12377_fr"])
 def test_fft_matches_definition_and_roundtrips(frname):
     q = O.FIELDS[frname].q
     rng = random.Random(4)
