@@ -1,22 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_fft.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -8
-timeout 300 python - <<'PY'
-import importlib, time, numpy as np, torch, sys
-sys.path.insert(0,'.')
-import gnark_crypto_b200
-fft = importlib.import_module("gnark-crypto_b200.fft")
-for logn in (20, 24):
-    n = 1 << logn
-    d = fft.NewDomain("bn254", n)
-    a = torch.randint(0, 2**59, (n*4,), dtype=torch.int64, device="cuda")
-    for _ in range(3): d.fft_device(a, False, 1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5): d.fft_device(a, False, 1)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)/5
-    print("bn254 fr FFT DIF n=2^%d: %.3f ms  (%.1f GB/s algorithmic at %d passes of 64 B/elt)" % (logn, ms, (logn-10+1)*n*64/ms/1e6, logn-10+1))
-    d.close()
-PY
+timeout 1700 python -m pytest tests -x -q -m gpu -p no:cacheprovider 2>&1 | tail -5
+timeout 300 python bench.py --curve bls12377_g1 --logn 22 --steps 3 --warmup 3 > gpurun_out/bench_bls12377g1_2e22.json 2>gpurun_out/v.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_bls12377g1_2e22.json')); print('bls12377_g1 2^22 c', d['config']['c'], 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'cpu', round(d['cpu_baseline']['value']))" || tail -3 gpurun_out/v.err
