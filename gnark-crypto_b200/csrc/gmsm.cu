@@ -417,36 +417,105 @@ static int check_nb_tasks(int nb_tasks) {
   return GMSM_OK;
 }
 
+// join the W window partials of D shards (host copy, shard-major) on the device of pipeline P0:
+// per-window sum over the shards, Horner, normalisation -> out_jac (host)
+static int join_partials(int curve, Pipeline& P0, void** d_gather, size_t* gather_cap, const unsigned char* h_part,
+                         size_t bytes, int D, uint64_t* out_jac) {
+  CurveInfo ci;
+  curve_info(curve, &ci);
+  CK(cudaSetDevice(P0.device));
+  if (*gather_cap < bytes) {
+    cudaFree(*d_gather); *d_gather = nullptr;
+    CK(cudaMalloc(d_gather, bytes));
+    *gather_cap = bytes;
+  }
+  CK(cudaMemcpyAsync(*d_gather, h_part, bytes, cudaMemcpyHostToDevice, P0.comp_st));
+  {
+    std::lock_guard<std::mutex> lk2(P0.ctx->mu);
+    if (int rc = vtable(curve)->finalize(P0.ctx, *d_gather, D, P0.d_out, P0.comp_st)) return rc;
+  }
+  CK(cudaMemcpyAsync(out_jac, P0.d_out, 12u * ci.coord_words, cudaMemcpyDeviceToHost, P0.comp_st));
+  CK(cudaStreamSynchronize(P0.comp_st));
+  return GMSM_OK;
+}
+
+// the devices listed in GMSM_DEVICES ("0,1,2,3"), empty if unset
+static std::vector<int> env_devices() {
+  std::vector<int> out;
+  if (const char* e = getenv("GMSM_DEVICES")) {
+    for (const char* q = e; *q;) {
+      char* end = nullptr;
+      long v = strtol(q, &end, 10);
+      if (end == q) break;
+      out.push_back((int)v);
+      q = (*end == ',') ? end + 1 : end;
+    }
+  }
+  return out;
+}
+
 // ---- resident bases ----
-struct gmsm_bases {
-  int curve = 0, device = 0;
-  size_t n = 0;
+// device >= 0: all bases on that device.  device == -1: the bases are sharded contiguously over the devices of
+// GMSM_DEVICES (one process driving several GPUs); a call then runs one host thread per shard.
+struct BaseShard {
+  int device = 0;
+  size_t lo = 0, hi = 0;
   void* d_points = nullptr;
   Pipeline pipe;
+  void* d_gather = nullptr;
+  size_t gather_cap = 0;
+};
+struct gmsm_bases {
+  int curve = 0;
+  size_t n = 0;
+  std::vector<BaseShard> shards;
   std::mutex mu;
 };
+
+extern "C" void gmsm_bases_free(gmsm_bases_t* b);
 
 extern "C" gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size_t n, int device) {
   CurveInfo ci;
   if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
-  if (check_device(device) != GMSM_OK) return nullptr;
-  cudaSetDevice(device);
-  gmsm_bases* b = new gmsm_bases();
-  b->curve = curve; b->device = device; b->n = n;
-  const size_t bytes = n * 8u * ci.coord_words;
-  if (cudaMalloc(&b->d_points, bytes ? bytes : 16) != cudaSuccess) { set_err(GMSM_ENOMEM, "cudaMalloc(%zu) for bases failed", bytes); delete b; return nullptr; }
-  if (bytes && cudaMemcpy(b->d_points, points, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-    set_err(GMSM_ECUDA, "H2D copy of bases failed"); cudaFree(b->d_points); delete b; return nullptr;
+  std::vector<int> devs;
+  if (device == -1) {
+    devs = env_devices();
+    if (devs.empty()) { set_err(GMSM_EINVAL, "device = -1 needs GMSM_DEVICES"); return nullptr; }
+  } else {
+    devs.push_back(device);
   }
-  if (pipeline_init(b->pipe, curve, device) != GMSM_OK) { cudaFree(b->d_points); delete b; return nullptr; }
+  for (int d : devs) if (check_device(d) != GMSM_OK) return nullptr;
+  const size_t ab = 8u * ci.coord_words;
+  gmsm_bases* b = new gmsm_bases();
+  b->curve = curve; b->n = n;
+  b->shards.resize(devs.size());
+  for (size_t d = 0; d < devs.size(); d++) {
+    BaseShard& sh = b->shards[d];
+    sh.device = devs[d];
+    sh.lo = n * d / devs.size();
+    sh.hi = n * (d + 1) / devs.size();
+    const size_t bytes = (sh.hi - sh.lo) * ab;
+    bool ok = cudaSetDevice(sh.device) == cudaSuccess && cudaMalloc(&sh.d_points, bytes ? bytes : 16) == cudaSuccess;
+    if (ok && bytes) ok = cudaMemcpy(sh.d_points, reinterpret_cast<const char*>(points) + sh.lo * ab, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) ok = pipeline_init(sh.pipe, curve, sh.device) == GMSM_OK;
+    if (!ok) {
+      std::string keep = g_err.empty() ? std::string("upload of bases failed (allocation or H2D copy)") : g_err;
+      gmsm_bases_free(b);
+      g_err = keep;
+      return nullptr;
+    }
+  }
   return b;
 }
 
 extern "C" void gmsm_bases_free(gmsm_bases_t* b) {
   if (!b) return;
-  cudaSetDevice(b->device);
-  pipeline_free(b->pipe);
-  cudaFree(b->d_points);
+  for (BaseShard& sh : b->shards) {
+    cudaSetDevice(sh.device);
+    pipeline_free(sh.pipe);
+    cudaFree(sh.d_points);
+    cudaFree(sh.d_gather);
+  }
   delete b;
 }
 
@@ -458,9 +527,40 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   std::lock_guard<std::mutex> lk(b->mu);
   CurveInfo ci;
   curve_info(b->curve, &ci);
+  const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words;
   if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
-  char* pts = reinterpret_cast<char*>(b->d_points) + offset * 8u * ci.coord_words;
-  return pipeline_run(b->pipe, pts, nullptr, scalars, n, out_jac);
+  // shards intersecting [offset, offset + n)
+  struct Job { BaseShard* sh; size_t a, e; };
+  std::vector<Job> jobs;
+  for (BaseShard& sh : b->shards) {
+    const size_t a = std::max(sh.lo, offset), e = std::min(sh.hi, offset + n);
+    if (a < e) jobs.push_back({&sh, a, e});
+  }
+  if (jobs.size() == 1) {
+    BaseShard& sh = *jobs[0].sh;
+    return pipeline_run(sh.pipe, reinterpret_cast<char*>(sh.d_points) + (jobs[0].a - sh.lo) * ab, nullptr, scalars, n, out_jac);
+  }
+  const int c = choose_c(ci.fr_bits, n);
+  const WindowPlan plan = make_plan(ci.fr_bits, c);
+  std::vector<unsigned char> h_part(jobs.size() * plan.nwin * xb);
+  std::vector<int> rcs(jobs.size(), GMSM_OK);
+  std::vector<std::string> errs(jobs.size());
+  {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < jobs.size(); k++) {
+      th.emplace_back([&, k]() {
+        const Job& j = jobs[k];
+        rcs[k] = pipeline_run(j.sh->pipe, reinterpret_cast<char*>(j.sh->d_points) + (j.a - j.sh->lo) * ab, nullptr,
+                              scalars + (j.a - offset) * 4, j.e - j.a, nullptr, c, h_part.data() + k * plan.nwin * xb);
+        if (rcs[k]) errs[k] = g_err;
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  for (size_t k = 0; k < jobs.size(); k++)
+    if (rcs[k]) return set_err(rcs[k], "device %d: %s", jobs[k].sh->device, errs[k].c_str());
+  BaseShard& s0 = *jobs[0].sh;
+  return join_partials(b->curve, s0.pipe, &s0.d_gather, &s0.gather_cap, h_part.data(), h_part.size(), (int)jobs.size(), out_jac);
 }
 
 // per-(curve, device) session of the host entry points: device buffers, streams and the engine context are kept
@@ -513,16 +613,7 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
   // devices: GMSM_DEVICES="0,1,2,3" shards one call over several GPUs of this process (one host thread per
   // device, the per-device window partials joined on the first one); default: the single GMSM_DEVICE (0)
-  std::vector<int> devs;
-  if (const char* e = getenv("GMSM_DEVICES")) {
-    for (const char* q = e; *q;) {
-      char* end = nullptr;
-      long v = strtol(q, &end, 10);
-      if (end == q) break;
-      devs.push_back((int)v);
-      q = (*end == ',') ? end + 1 : end;
-    }
-  }
+  std::vector<int> devs = env_devices();
   if (devs.empty()) {
     int device = 0;
     if (const char* e = getenv("GMSM_DEVICE")) device = atoi(e);
@@ -567,19 +658,7 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
     if (rcs[d]) return set_err(rcs[d], "device %d: %s", devs[d], errs[d].c_str());
   // join on the first device: per-window sum over the D shards, Horner, normalisation
   Session& S0 = *ss[0];
-  CK(cudaSetDevice(devs[0]));
-  if (S0.gather_cap < h_part.size()) {
-    cudaFree(S0.d_gather); S0.d_gather = nullptr;
-    CK(cudaMalloc(&S0.d_gather, h_part.size()));
-    S0.gather_cap = h_part.size();
-  }
-  CK(cudaMemcpyAsync(S0.d_gather, h_part.data(), h_part.size(), cudaMemcpyHostToDevice, S0.pipe.comp_st));
-  {
-    std::lock_guard<std::mutex> lk2(S0.pipe.ctx->mu);
-    if (int rc = vtable(curve)->finalize(S0.pipe.ctx, S0.d_gather, (int)D, S0.pipe.d_out, S0.pipe.comp_st)) return rc;
-  }
-  CK(cudaMemcpyAsync(out_jac, S0.pipe.d_out, jb, cudaMemcpyDeviceToHost, S0.pipe.comp_st));
-  CK(cudaStreamSynchronize(S0.pipe.comp_st));
+  if (int rc = join_partials(curve, S0.pipe, &S0.d_gather, &S0.gather_cap, h_part.data(), h_part.size(), (int)D, out_jac)) return rc;
   int launches = 1;
   for (size_t d = 0; d < D; d++) launches += ss[d]->pipe.last_launches;
   g_last_oneshot_launches = launches;

@@ -87,6 +87,8 @@ int gmsm_last_oneshot_launches(void);
 /* ---- 2. resident bases (the prover flow: SRS / proving-key points are static, kzg.Commit
  * ecc/bn254/kzg/kzg.go:159-176 passes pk.G1[:len(p)]) ---- */
 typedef struct gmsm_bases gmsm_bases_t;
+/* device >= 0: all bases on that GPU; device == -1: sharded contiguously over the GPUs listed in GMSM_DEVICES
+ * (every call then runs one host thread per shard and joins the window partials on the first one) */
 gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size_t n, int device);
 /* MSM over bases[offset, offset+n) with host scalars */
 int gmsm_bases_multiexp(gmsm_bases_t* bases, size_t offset, const uint64_t* scalars, size_t n,

@@ -88,6 +88,18 @@ def test_in_process_multi_device_one_shot(monkeypatch):
         monkeypatch.setenv("GMSM_DEVICES", ",".join(str(d) for d in range(ndev)))
         got = Aff().MultiExp(pts, s, pkg.MultiExpConfig())
         assert np.array_equal(got.limbs, want), g
+        # resident bases sharded over the same devices (device = -1), full range and a sub-range that
+        # straddles shard boundaries
+        from importlib import import_module
+
+        mx = import_module("gnark-crypto_b200.multiexp")
+        rb = mx.ResidentBases(g, pts, device=-1)
+        w = pts.shape[1]
+        assert np.array_equal(rb.MultiExp(s)[:w], want), g
+        lo, m = n // 5, n // 2
+        want_sub, _, _, _ = cref.msm(g, pts[lo : lo + m], s[:m], c=0, nthreads=8)
+        assert np.array_equal(rb.MultiExp(s[:m], offset=lo)[:w], want_sub), g
+        rb.close()
         monkeypatch.delenv("GMSM_DEVICES")
         got1 = Aff().MultiExp(pts, s, pkg.MultiExpConfig())
         assert np.array_equal(got1.limbs, want), g
