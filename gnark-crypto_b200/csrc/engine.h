@@ -51,7 +51,7 @@ struct gmsm_ctx {
   void* carries[2] = {nullptr, nullptr};
   uint32_t* carry_ids[2] = {nullptr, nullptr};
   void* seg[2] = {nullptr, nullptr};
-  // batch-affine accumulation (affine_kernels.cuh); enabled per context (GMSM_AFFINE, default on)
+  // batch-affine accumulation variant (affine_kernels.cuh); selected per context with GMSM_AFFINE=1 (default off)
   bool affine = false;
   void* aff_buf[2] = {nullptr, nullptr};   // level outputs, ping-pong (affine points)
   void* aff_pref = nullptr;                // running products before each denominator
