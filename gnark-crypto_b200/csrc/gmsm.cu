@@ -739,6 +739,13 @@ extern "C" int gmsm_batch_scalar_mul(gmsm_curve_t curve, const uint64_t* base_af
 // ------------------------------------------------------------------------------------------
 // test hooks
 // ------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {   // frees on every exit path (the CK macro returns early on errors)
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
 extern "C" int gmsm_test_op(gmsm_curve_t curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
   int wa = 0, wb = 0, wo = 0;
   const GroupVTable* vt = vtable(curve);
@@ -746,16 +753,16 @@ extern "C" int gmsm_test_op(gmsm_curve_t curve, int op, const uint32_t* a, const
   vt->test_op_sizes(op, &wa, &wb, &wo);
   if (wo == 0) return set_err(GMSM_EINVAL, "unknown op %d", op);
   if (n == 0) return GMSM_OK;
-  uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
-  CK(cudaMalloc(&da, n * wa * 4));
-  CK(cudaMalloc(&db, n * std::max(wb, 1) * 4));
-  CK(cudaMalloc(&dout, n * wo * 4));
+  DevBuf ba, bb, bo;
+  CK(cudaMalloc(&ba.p, n * wa * 4));
+  CK(cudaMalloc(&bb.p, n * std::max(wb, 1) * 4));
+  CK(cudaMalloc(&bo.p, n * wo * 4));
+  uint32_t *da = ba.as<uint32_t>(), *db = bb.as<uint32_t>(), *dout = bo.as<uint32_t>();
   CK(cudaMemcpy(da, a, n * wa * 4, cudaMemcpyHostToDevice));
   if (wb) CK(cudaMemcpy(db, b, n * wb * 4, cudaMemcpyHostToDevice));
   if (int rc = vt->test_op(op, da, db, dout, n)) return rc;
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, dout, n * wo * 4, cudaMemcpyDeviceToHost));
-  cudaFree(da); cudaFree(db); cudaFree(dout);
   return GMSM_OK;
 }
 
@@ -765,14 +772,14 @@ extern "C" int gmsm_test_digits(gmsm_curve_t curve, int c, const uint64_t* scala
   if (c < 2 || c > 24) return set_err(GMSM_EINVAL, "c out of range");
   if (n == 0) return GMSM_OK;
   WindowPlan p = make_plan(ci.fr_bits, c);
-  void* ds = nullptr;
-  uint32_t* dout = nullptr;
-  CK(cudaMalloc(&ds, n * 32));
-  CK(cudaMalloc(&dout, n * (size_t)p.nwin * 4));
+  DevBuf bs, bo;
+  CK(cudaMalloc(&bs.p, n * 32));
+  CK(cudaMalloc(&bo.p, n * (size_t)p.nwin * 4));
+  void* ds = bs.p;
+  uint32_t* dout = bo.as<uint32_t>();
   CK(cudaMemcpy(ds, scalars, n * 32, cudaMemcpyHostToDevice));
   if (int rc = vtable(curve)->digits_dump(ds, n, p.c, p.nwin, dout)) return rc;
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, dout, n * (size_t)p.nwin * 4, cudaMemcpyDeviceToHost));
-  cudaFree(ds); cudaFree(dout);
   return GMSM_OK;
 }

@@ -1,29 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dist.py -x -q -m gpu -p no:cacheprovider 2>&1 | tail -4
-timeout 300 python - <<'PY'
-import importlib, os, sys, time, numpy as np, torch
-sys.path.insert(0,'.')
-pkg = importlib.import_module("gnark_crypto_b200")
-mx = importlib.import_module("gnark-crypto_b200.multiexp")
-bench = importlib.import_module("bench")
-g, n = "bn254_g1", 1 << 24
-eng = pkg.Engine(g, n)
-base = bench._generator_limbs(g)
-pts = torch.empty(n * 8, dtype=torch.int64).pin_memory(); pts.copy_(eng.generate_multiples(base, 1, n).cpu())
-sc = torch.empty(n * 4, dtype=torch.int64).pin_memory(); sc.copy_(torch.from_numpy(bench.synth_scalars(n, 254, 7).view(np.int64).reshape(-1)))
-hp, hs = pts.numpy().view(np.uint64).reshape(n, 8), sc.numpy().view(np.uint64).reshape(n, 4)
-eng.close()
-ref = None
-for devs in ("0", "0,1"):
-    os.environ["GMSM_DEVICES"] = devs
-    rb = mx.ResidentBases(g, hp, device=-1)
-    out = rb.MultiExp(hs); out = rb.MultiExp(hs)
-    t0 = time.perf_counter()
-    for _ in range(5): out = rb.MultiExp(hs)
-    dt = (time.perf_counter() - t0) / 5
-    rb.close()
-    ref = out if ref is None else ref
-    assert np.array_equal(out, ref)
-    print("resident bases, GMSM_DEVICES=%s: %.2f ms per call (2^24 scalars from pinned host memory) -> %.1f M scalar-muls/s" % (devs, dt * 1e3, n / dt / 1e6))
-PY
+timeout 900 python bench.py --logn 26 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_bn254g1_2e26.json 2>gpurun_out/v.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_bn254g1_2e26.json')); print('bn254_g1 2^26 c', d['config']['c'], 'ms', round(d['ms_per_step'],2), 'M/s', round(d['value']/1e6,1), 'e2e', round(d['e2e']['ms_per_step'],2), 'res', round(d['e2e_resident_bases']['ms_per_step'],2), {k:round(v,2) for k,v in d['stages_ms'].items()})" || tail -3 gpurun_out/v.err
+timeout 600 python bench.py --curve bls12381_g2 --logn 20 --steps 3 --warmup 3 > gpurun_out/bench_bls12381g2_2e20.json 2>gpurun_out/v2.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_bls12381g2_2e20.json')); print('bls12381_g2 2^20 c', d['config']['c'], 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'cpu', round(d['cpu_baseline']['value']))" || tail -3 gpurun_out/v2.err
