@@ -40,19 +40,33 @@ GMSM_D T load_vec(const T* p) {
   }
   return r;
 }
+// read-only path (points and scalars are never written during an MSM).  Objects of a multiple of 32 bytes --
+// affine points (64 / 96 / 128 / 192 B), scalars (32 B) -- are fetched with 256-bit loads
+// (ld.global.nc.v8.b32 -> LDG.E.256 on sm_100a); they are 32-byte aligned in device memory.
 template <class T>
-GMSM_D T load_vec_ro(const T* p) {  // read-only path (points are never written during an MSM)
+GMSM_D T load_vec_ro(const T* p) {
   static_assert(sizeof(T) % 16 == 0, "16-byte granules");
   T r;
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-  const uint4* s = reinterpret_cast<const uint4*>(p);
+  if constexpr (sizeof(T) % 32 == 0) {
+    const char* s = reinterpret_cast<const char*>(p);
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
-    uint4 v = __ldg(s + i);
-    w[4 * i + 0] = v.x;
-    w[4 * i + 1] = v.y;
-    w[4 * i + 2] = v.z;
-    w[4 * i + 3] = v.w;
+    for (int i = 0; i < (int)(sizeof(T) / 32); i++) {
+      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[8 * i]), "=r"(w[8 * i + 1]), "=r"(w[8 * i + 2]), "=r"(w[8 * i + 3]), "=r"(w[8 * i + 4]),
+                     "=r"(w[8 * i + 5]), "=r"(w[8 * i + 6]), "=r"(w[8 * i + 7])
+                   : "l"(s + 32 * i));
+    }
+  } else {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
+      uint4 v = __ldg(s + i);
+      w[4 * i + 0] = v.x;
+      w[4 * i + 1] = v.y;
+      w[4 * i + 2] = v.z;
+      w[4 * i + 3] = v.w;
+    }
   }
   return r;
 }
