@@ -29,8 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CURVE_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255, "bls12377_g1": 253}
-AFF_BYTES = {"bn254_g1": 64, "bn254_g2": 128, "bls12381_g1": 96, "bls12381_g2": 192, "bls12377_g1": 96}
+CURVE_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255, "bls12377_g1": 253, "bls12377_g2": 253}
+AFF_BYTES = {"bn254_g1": 64, "bn254_g2": 128, "bls12381_g1": 96, "bls12381_g2": 192, "bls12377_g1": 96, "bls12377_g2": 192}
 FR_MOD = {
     254: 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
     255: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,

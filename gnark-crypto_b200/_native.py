@@ -17,7 +17,7 @@ GMSM_OK, GMSM_EINVAL, GMSM_ECUDA, GMSM_ENOMEM, GMSM_ENODEV = 0, 1, 2, 3, 4
 # every symbol include/gmsm.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gmsm_last_error", "gmsm_version", "gmsm_affine_bytes", "gmsm_scalar_bytes", "gmsm_jac_bytes", "gmsm_xyzz_bytes",
-    "gmsm_bn254_g1_multiexp", "gmsm_bn254_g2_multiexp", "gmsm_bls12381_g1_multiexp", "gmsm_bls12381_g2_multiexp", "gmsm_bls12377_g1_multiexp",
+    "gmsm_bn254_g1_multiexp", "gmsm_bn254_g2_multiexp", "gmsm_bls12381_g1_multiexp", "gmsm_bls12381_g2_multiexp", "gmsm_bls12377_g1_multiexp", "gmsm_bls12377_g2_multiexp",
     "gmsm_multiexp", "gmsm_choose_window_bits", "gmsm_multiexp_window_sums", "gmsm_last_oneshot_launches", "gmsm_bases_upload", "gmsm_bases_multiexp", "gmsm_bases_free",
     "gmsm_ctx_create", "gmsm_ctx_destroy", "gmsm_ctx_window_bits", "gmsm_ctx_num_windows", "gmsm_ctx_workspace_bytes",
     "gmsm_ctx_last_launches", "gmsm_ctx_msm_device", "gmsm_ctx_window_sums_device", "gmsm_ctx_finalize_device",
@@ -48,7 +48,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f).restype = sz
         getattr(L, f).argtypes = [i32]
     for f in ("gmsm_bn254_g1_multiexp", "gmsm_bn254_g2_multiexp", "gmsm_bls12381_g1_multiexp", "gmsm_bls12381_g2_multiexp",
-              "gmsm_bls12377_g1_multiexp"):
+              "gmsm_bls12377_g1_multiexp", "gmsm_bls12377_g2_multiexp"):
         getattr(L, f).argtypes = [vp, vp, sz, i32, vp]
     L.gmsm_multiexp.argtypes = [i32, vp, vp, sz, i32, vp]
     L.gmsm_choose_window_bits.argtypes = [i32, sz]

@@ -111,6 +111,6 @@ struct GroupVTable {
   int (*digits_dump)(const void* d_scalars, size_t n, int c, int nwin, uint32_t* dout);
   int (*batch_scalar_mul)(const void* d_table, const void* d_scalars, size_t n, int c, int nwin, void* d_out, cudaStream_t);
 };
-extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1;
+extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1, vt_bls12377_g2;
 
 }  // namespace gmsm

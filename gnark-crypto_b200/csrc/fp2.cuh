@@ -1,4 +1,5 @@
-// Quadratic extension Fp2 = Fp[u]/(u^2+1) for G2 (both bn254 and bls12-381 use u^2 = -1).
+// Quadratic extension Fp2 = Fp[u]/(u^2 - beta) for G2: beta = -1 for bn254 and bls12-381, beta = -5 for
+// bls12-377 (P::FP2_NONRES; ecc/bls12-377/internal/fptower/e2_bls377.go:12-80).
 //
 // Replaces (reference): E2.Mul/Square ecc/bn254/internal/fptower/e2_bn254.go:28-51 (asm
 // e2_amd64.s:393,548), Add/Sub/Double/Neg e2.go:104-126, Inverse e2_bn254.go:61-73; identical
@@ -25,9 +26,15 @@ template <class P> GMSM_HD Fp2<P> f_sub(const Fp2<P>& a, const Fp2<P>& b) { retu
 template <class P> GMSM_HD Fp2<P> f_dbl(const Fp2<P>& a) { return Fp2<P>{fp_dbl(a.a0), fp_dbl(a.a1)}; }
 template <class P> GMSM_HD Fp2<P> f_neg(const Fp2<P>& a) { return Fp2<P>{fp_neg(a.a0), fp_neg(a.a1)}; }
 
-// Karatsuba, 3 fp.Mul (e2_bn254.go:28-38)
+template <class P>
+GMSM_HD Fp<P> fp_mul_by5(const Fp<P>& c) {  // fp.MulBy5
+  return fp_add(fp_dbl(fp_dbl(c)), c);
+}
+
+// Karatsuba, 3 fp.Mul (e2_bn254.go:28-38; e2_bls377.go:12-23 with the a1*b1 term times 5)
 template <class P>
 GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
+  static_assert(P::FP2_NONRES == -1 || P::FP2_NONRES == -5, "supported quadratic non-residues");
   Fp<P> a = fp_add(x.a0, x.a1);
   Fp<P> b = fp_add(y.a0, y.a1);
   a = fp_mul(a, b);
@@ -35,17 +42,19 @@ GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
   Fp<P> c = fp_mul(x.a1, y.a1);
   Fp2<P> z;
   z.a1 = fp_sub(fp_sub(a, b), c);
+  if (P::FP2_NONRES == -5) c = fp_mul_by5(c);
   z.a0 = fp_sub(b, c);
   return z;
 }
 
-// 2 fp.Mul (e2_bn254.go:41-51)
+// 2 fp.Mul (e2_bn254.go:41-51; e2_bls377.go:26-38: (a0+a1)(a0-5a1) + 4 a0 a1)
 template <class P>
 GMSM_HD Fp2<P> f_sqr(const Fp2<P>& x) {
   Fp<P> a = fp_add(x.a0, x.a1);
-  Fp<P> b = fp_sub(x.a0, x.a1);
+  Fp<P> b = (P::FP2_NONRES == -5) ? fp_sub(x.a0, fp_mul_by5(x.a1)) : fp_sub(x.a0, x.a1);
   a = fp_mul(a, b);
   b = fp_dbl(fp_mul(x.a0, x.a1));
+  if (P::FP2_NONRES == -5) a = fp_add(a, fp_dbl(b));
   return Fp2<P>{a, b};
 }
 
@@ -54,6 +63,7 @@ template <class P>
 GMSM_HD Fp2<P> f_inv(const Fp2<P>& x) {
   Fp<P> t0 = fp_sqr(x.a0);
   Fp<P> t1 = fp_sqr(x.a1);
+  if (P::FP2_NONRES == -5) t1 = fp_mul_by5(t1);   // norm = a0^2 - beta a1^2
   t0 = fp_add(t0, t1);
   t1 = fp_inv(t0);
   return Fp2<P>{fp_mul(x.a0, t1), fp_neg(fp_mul(x.a1, t1))};

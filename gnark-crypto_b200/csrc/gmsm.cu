@@ -48,6 +48,7 @@ static bool curve_info(int curve, CurveInfo* ci) {
     case GMSM_BLS12381_G1: *ci = {bls12381_g1::F::N, bls12381_fr::BITS}; return true;
     case GMSM_BLS12381_G2: *ci = {bls12381_g2::F::N, bls12381_fr::BITS}; return true;
     case GMSM_BLS12377_G1: *ci = {bls12377_g1::F::N, bls12377_fr::BITS}; return true;
+    case GMSM_BLS12377_G2: *ci = {bls12377_g2::F::N, bls12377_fr::BITS}; return true;
   }
   return false;
 }
@@ -64,6 +65,7 @@ static const GroupVTable* vtable(int curve) {
     case GMSM_BLS12381_G1: return &vt_bls12381_g1;
     case GMSM_BLS12381_G2: return &vt_bls12381_g2;
     case GMSM_BLS12377_G1: return &vt_bls12377_g1;
+    case GMSM_BLS12377_G2: return &vt_bls12377_g2;
   }
   return nullptr;
 }
@@ -670,6 +672,7 @@ extern "C" int gmsm_bn254_g2_multiexp(const uint64_t* p, const uint64_t* s, size
 extern "C" int gmsm_bls12381_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[18]) { return gmsm_multiexp(GMSM_BLS12381_G1, p, s, n, t, out); }
 extern "C" int gmsm_bls12381_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BLS12381_G2, p, s, n, t, out); }
 extern "C" int gmsm_bls12377_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[18]) { return gmsm_multiexp(GMSM_BLS12377_G1, p, s, n, t, out); }
+extern "C" int gmsm_bls12377_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BLS12377_G2, p, s, n, t, out); }
 
 // ------------------------------------------------------------------------------------------
 // base generator

@@ -31,6 +31,7 @@ using bls12381_g1 = GroupT<2, bls12381_fp, bls12381_fr, false>;
 using bls12381_g2 = GroupT<3, bls12381_fp, bls12381_fr, true>;
 // next-row N4 (pure parametrisation): bls12-377 G1, ecc/bls12-377/g1.go, fr 253 bits
 using bls12377_g1 = GroupT<4, bls12377_fp, bls12377_fr, false>;
+using bls12377_g2 = GroupT<5, bls12377_fp, bls12377_fr, true>;   // Fp2 with u^2 = -5
 
 // word (u32) counts
 template <class G> constexpr int coord_words() { return G::F::N; }

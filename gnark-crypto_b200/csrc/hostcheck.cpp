@@ -24,6 +24,7 @@ extern "C" int hostcheck_op(int curve, int op, const uint32_t* a, const uint32_t
     case 2: return run<bls12381_g1>(op, a, b, o, n);
     case 3: return run<bls12381_g2>(op, a, b, o, n);
     case 4: return run<bls12377_g1>(op, a, b, o, n);
+    case 5: return run<bls12377_g2>(op, a, b, o, n);
   }
   return 1;
 }

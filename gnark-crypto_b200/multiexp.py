@@ -22,9 +22,9 @@ import numpy as np
 
 from . import _native
 
-CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4}
+CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5}
 # u64 words: (coordinate limbs L, coordinates per point-coordinate: 1 = Fp, 2 = Fp2)
-_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1)}
+_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1), 5: (6, 2)}
 
 
 class MultiExpError(Exception):
@@ -304,7 +304,7 @@ def test_op(curve: str, op: int, a: np.ndarray, b: np.ndarray, out_words: int) -
 def test_digits(curve: str, c: int, scalars: np.ndarray) -> np.ndarray:
     scalars = _as_u64(scalars, 4, "scalars")
     n = scalars.shape[0]
-    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253}[CURVES[curve]]
+    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253}[CURVES[curve]]
     W = (bits + c - 1) // c
     out = np.zeros((W, n), dtype=np.uint32)
     rc = _native.lib().gmsm_test_digits(CURVES[curve], c, scalars.ctypes.data, n, out.ctypes.data)

@@ -40,7 +40,8 @@ typedef enum {
   GMSM_BN254_G2 = 1,
   GMSM_BLS12381_G1 = 2,
   GMSM_BLS12381_G2 = 3,
-  GMSM_BLS12377_G1 = 4   /* next-row N4: ecc/bls12-377 (G1 only; its G2 tower has u^2 = -5) */
+  GMSM_BLS12377_G1 = 4,  /* next-row N4: ecc/bls12-377 */
+  GMSM_BLS12377_G2 = 5   /* its Fp2 tower has u^2 = -5 (e2_bls377.go) */
 } gmsm_curve_t;
 
 enum {
@@ -73,6 +74,8 @@ int gmsm_bls12381_g2_multiexp(const uint64_t* points, const uint64_t* scalars, s
                               uint64_t out_jac[36]);
 int gmsm_bls12377_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
                               uint64_t out_jac[18]);   /* ecc/bls12-377/multiexp.go:32 */
+int gmsm_bls12377_g2_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[36]);
 int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n,
                   int nb_tasks, uint64_t* out_jac);
 /* sharded calls with one process per GPU: every process runs its shard through the pipelined engine and gets the W

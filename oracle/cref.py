@@ -12,8 +12,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libmsmref.so")
 
-CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4}
-AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12}  # u64 words per affine point
+CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5}
+AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12, 5: 24}  # u64 words per affine point
 
 _lib = None
 
@@ -69,7 +69,7 @@ def partition_scalars(curve, scalars: np.ndarray, c: int) -> np.ndarray:
     cid = _cid(curve)
     scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
     n = scalars.shape[0]
-    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253}[cid]
+    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253}[cid]
     W = (bits + c - 1) // c
     out = np.zeros((W, n), dtype=np.uint32)
     rc = lib().ref_partition_scalars(cid, _p(scalars), n, c, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))

@@ -225,9 +225,11 @@ class Fp2Ops:
 
     ext = 2
 
-    def __init__(self, field: Field):
+    def __init__(self, field: Field, nonres: int = -1):
+        # u^2 = nonres: -1 for bn254 / bls12-381, -5 for bls12-377 (e2_bls377.go:12-80)
         self.f = field
         self.q = field.q
+        self.beta = nonres
         self.zero = (0, 0)
         self.one = (1, 0)
 
@@ -249,17 +251,17 @@ class Fp2Ops:
         ac = a[0] * b[0] % q
         bd = a[1] * b[1] % q
         t = (a[0] + a[1]) * (b[0] + b[1]) % q
-        return ((ac - bd) % q, (t - ac - bd) % q)
+        return ((ac + self.beta * bd) % q, (t - ac - bd) % q)
 
     def sqr(self, a):
         # e2_bn254.go:41-51
         q = self.q
-        return ((a[0] + a[1]) * (a[0] - a[1]) % q, (2 * a[0] * a[1]) % q)
+        return ((a[0] * a[0] + self.beta * a[1] * a[1]) % q, (2 * a[0] * a[1]) % q)
 
     def inv(self, a):
         # e2_bn254.go:61-73
         q = self.q
-        n = (a[0] * a[0] + a[1] * a[1]) % q
+        n = (a[0] * a[0] - self.beta * a[1] * a[1]) % q
         ni = 0 if n == 0 else pow(n, -1, q)
         return (a[0] * ni % q, (-a[1] * ni) % q)
 
@@ -554,6 +556,24 @@ def _mk_groups():
         (
             81937999373150964239938255573465948239988671502647976594219695644855304257327692006745978603320413799295628339695,
             241266749859715473739788878240585681733927191168601896383759122102112907357779751001206799952863815012735208165030,
+        ),
+    )
+    # ecc/bls12-377/bls12-377.go:10,103-105,111-114 : twist Y^2 = X^3 + 1/u, u^2 = -5
+    K2 = Fp2Ops(FIELDS["bls12377_fp"], nonres=-5)
+    g["bls12377_g2"] = Group(
+        "bls12377_g2",
+        K2,
+        FIELDS["bls12377_fr"],
+        K2.inv((0, 1)),
+        (
+            (
+                233578398248691099356572568220835526895379068987715365179118596935057653620464273615301663571204657964920925606294,
+                140913150380207355837477652521042157274541796891053068589147167627541651775299824604154852141315666357241556069118,
+            ),
+            (
+                63160294768292073209381361943935198908131692476676907196754037919244929611450776219210369229519898517858833747423,
+                149157405641012693445398062341192467754805999074082136895788947234480009303640899064710353187729182149407503257491,
+            ),
         ),
     )
     return g

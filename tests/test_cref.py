@@ -68,7 +68,7 @@ def test_generate_multiples_and_scalar_mul(g):
 
 
 @pytest.mark.parametrize("g,n,cs", [("bn254_g1", 300, [2, 5, 8, 13, 16, 18]), ("bls12381_g1", 120, [4, 16]),
-                                     ("bn254_g2", 100, [5, 16]), ("bls12381_g2", 40, [7]), ("bls12377_g1", 120, [5, 16])])
+                                     ("bn254_g2", 100, [5, 16]), ("bls12381_g2", 40, [7]), ("bls12377_g1", 120, [5, 16]), ("bls12377_g2", 60, [6])])
 def test_msm_matches_python_oracle(g, n, cs):
     G = O.GROUPS[g]
     base = G.encode_affine([G.gen])[0]

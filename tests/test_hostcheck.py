@@ -25,7 +25,7 @@ def hc():
 
 def _runner(hc, g):
     cid = list(O.GROUPS).index(g)
-    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1"]
+    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1", "bls12377_g2"]
 
     def run(op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)

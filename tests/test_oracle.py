@@ -164,7 +164,7 @@ def _inputs(G, n, seed, n_inf=0):
     return pts, ks
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bn254_g2", "bls12377_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bn254_g2", "bls12377_g1", "bls12377_g2"])
 def test_msm_all_c_agree(g):
     # multiexp_test.go:95-126 : 73 points, 4 random ones set to infinity, every c agrees
     G = O.GROUPS[g]
