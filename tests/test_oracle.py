@@ -86,25 +86,12 @@ def test_bls12381_g1_hash_vectors_known_answer():
         assert G.scalar_mul(G.aff_add(Q0, Q1), 0xD201000000010001) == P
 
 
-@pytest.mark.parametrize("curve,g", [("bn254", "bn254_g2"), ("bls12381", "bls12381_g2"), ("bls12377", "bls12377_g2")])
+@pytest.mark.parametrize("curve,g", [("bn254", "bn254_g2"), ("bls12381", "bls12381_g2")])
 def test_g2_vectors_on_twist(curve, g):
     G = O.GROUPS[g]
     vec = GOLD[curve]["vectors"]
     n = 0
     for c in vec["hashToG2Vector"] + vec["encodeToG2Vector"]:
-        for k in ("P", "Q0", "Q1", "Q"):
-            if k in c:
-                assert G.is_on_curve(_pt(G, c[k]))
-                n += 1
-    assert n >= 20
-
-
-def test_bls12377_g1_vectors_on_curve():
-    # next-row N4: ecc/bls12-377/hash_vectors_test.go -- every listed point lies on Y^2 = X^3 + 1
-    G = O.GROUPS["bls12377_g1"]
-    vec = GOLD["bls12377"]["vectors"]
-    n = 0
-    for c in vec["hashToG1Vector"] + vec["encodeToG1Vector"]:
         for k in ("P", "Q0", "Q1", "Q"):
             if k in c:
                 assert G.is_on_curve(_pt(G, c[k]))
