@@ -70,6 +70,7 @@ struct gmsm_ctx {
   int last_launches = 0;
   bool profiling = false;
   cudaEvent_t ev[9] = {};
+  int split_w = 2;                     // windows scattered before the accumulate starts (GMSM_SPLIT_W)
   cudaStream_t aux = nullptr;          // auxiliary stream: scatter of the later windows under the accumulate
   cudaEvent_t ev_split[2] = {};
   float stage_ms[8] = {};

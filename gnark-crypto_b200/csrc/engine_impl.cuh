@@ -60,7 +60,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   // and run underneath the first part of the accumulate kernel (multiplier-bound, L2 idle) -- see K2.
   // (measured: -1.3 ms at bn254 G1 2^24, -0.5 ms bls12-381 G1; +0.8 ms for G2, whose 255-register accumulate
   // blocks leave no room for co-resident scatter blocks -> G1 groups only)
-  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? 2 : p.nwin;
+  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->split_w, p.nwin) : p.nwin;
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 8u);
     auto scatter = [&](int j, cudaStream_t s) {

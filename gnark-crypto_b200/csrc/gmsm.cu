@@ -193,6 +193,7 @@ extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, 
   // 46.3 ms vs 42.1 ms at bn254 G1 n=2^24, profiles/r01_ncu_affine_*).
   ctx->affine = false;
   if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
+  if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = v; }
   ctx->plan = make_plan(ci.fr_bits, c);
   if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
     set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 32-bit entry index; shard the MSM", max_n, ctx->plan.nwin);
