@@ -158,7 +158,7 @@ def run_reference(args, rank, world):
         "data": "synthetic", "config": {"workload": "%s MultiExp n=2^%d per GPU (configs[1]); each step a 2^%d sample" % (g, args.logn, logs),
                                         "c": used_c, "threads": cores},
         "cpu_baseline": {"value": val, "unit": "scalar-muls/s", "cores": cores, "kind": "port",
-                         "sample": "n=2^%d of the same workload, C port of the reference algorithm (bestC c=%d, ext-Jacobian buckets)" % (logs, used_c)},
+                         "sample": "n=2^%d of the same workload, C port of the reference algorithm (bestC c=%d, batch-affine buckets as in getChunkProcessorG1)" % (logs, used_c)},
         "e2e": {"value": val, "unit": "scalar-muls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -391,7 +391,7 @@ def main():
             raise SystemExit("bench.py: GPU result differs from the CPU oracle on the baseline sample")
         line["cpu_baseline"] = {"value": ns / best, "unit": "scalar-muls/s", "cores": cores, "kind": "port",
                                 "sample": "first 2^%d points/scalars of the same workload; C port of the reference algorithm "
-                                          "(bestC c=%d, %d sub-MSMs, ext-Jacobian buckets), best of 2, GPU result on the sample "
+                                          "(bestC c=%d, %d sub-MSMs, batch-affine buckets as in getChunkProcessorG1), best of 2, GPU result on the sample "
                                           "bit-exact" % (logs, used_c, leaves)}
     if rank == 0:
         print(json.dumps(line))

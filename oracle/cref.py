@@ -40,6 +40,12 @@ def lib():
     return _lib
 
 
+def set_batch_affine(on: bool):
+    """processor selection of the port: True (default) = the reference's getChunkProcessorG1 (batch-affine buckets
+    for 10 <= c <= 16), False = extended-Jacobian buckets everywhere"""
+    lib().ref_set_batch_affine(1 if on else 0)
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
 

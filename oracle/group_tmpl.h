@@ -226,6 +226,112 @@ static void GP(process_chunk)(int c_eff, const GP(aff)* points, const uint32_t* 
   free(buckets);
 }
 
+/* batchAddG1Affine g1.go:1122-1182: R[j] += P[j] for cnt independent affine pairs (no infinity, distinct x)
+ * with one shared inversion (Montgomery's trick) */
+static void GP(batch_add_affine)(GP(aff)** R, const GP(aff)* P, int cnt, K(t)* lambda, K(t)* lambdain) {
+  if (cnt == 0) return;
+  for (int j = 0; j < cnt; j++) K(sub)(&lambdain[j], &P[j].x, &R[j]->x);
+  K(t) acc;
+  K(set_one)(&lambda[0]);
+  acc = lambdain[0];
+  for (int i = 1; i < cnt; i++) { lambda[i] = acc; K(mul)(&acc, &acc, &lambdain[i]); }
+  K(inv)(&acc, &acc);
+  for (int i = cnt - 1; i > 0; i--) { K(mul)(&lambda[i], &lambda[i], &acc); K(mul)(&acc, &acc, &lambdain[i]); }
+  lambda[0] = acc;
+  for (int j = 0; j < cnt; j++) {
+    K(t) t;
+    GP(aff) Q;
+    K(sub)(&t, &P[j].y, &R[j]->y);
+    K(mul)(&lambda[j], &lambda[j], &t);
+    K(sqr)(&Q.x, &lambda[j]);
+    K(sub)(&Q.x, &Q.x, &R[j]->x);
+    K(sub)(&Q.x, &Q.x, &P[j].x);
+    K(sub)(&t, &R[j]->x, &Q.x);
+    K(mul)(&Q.y, &lambda[j], &t);
+    K(sub)(&Q.y, &Q.y, &R[j]->y);
+    *R[j] = Q;
+  }
+}
+
+/* batch sizes of the generated processors, multiexp_affine.go:298-338 (0 = no batch-affine processor) */
+static inline int GP(batch_size)(int c) {
+  switch (c) { case 10: return 80; case 11: return 150; case 12: return 200; case 13: return 350; case 14: return 400;
+               case 15: return 500; case 16: return 640; default: return 0; }
+}
+
+/* processChunkG1BatchAffine multiexp_affine.go:24-231: affine buckets, batches of independent additions sharing
+ * one inversion, a queue for conflicting buckets, extended-Jacobian fallback buckets for doublings / a full queue */
+typedef struct { uint32_t bucket; GP(aff) point; } GP(batch_op);
+static void GP(process_chunk_batch_affine)(int c_eff, int batch, const GP(aff)* points, const uint32_t* digits, size_t n,
+                                           GP(xyzz)* total) {
+  const size_t nb = (size_t)1 << (c_eff - 1);
+  GP(aff)* buckets = (GP(aff)*)calloc(nb, sizeof(GP(aff)));          /* infinity = (0,0) */
+  GP(xyzz)* bucketsJE = (GP(xyzz)*)malloc(nb * sizeof(GP(xyzz)));
+  for (size_t k = 0; k < nb; k++) GP(xyzz_set_inf)(&bucketsJE[k]);
+  unsigned char* in_batch = (unsigned char*)calloc(nb, 1);            /* bitSet */
+  GP(aff)** R = (GP(aff)**)malloc(sizeof(GP(aff)*) * batch);
+  GP(aff)* P = (GP(aff)*)malloc(sizeof(GP(aff)) * batch);
+  uint32_t* batch_ids = (uint32_t*)malloc(sizeof(uint32_t) * batch);
+  GP(batch_op)* queue = (GP(batch_op)*)malloc(sizeof(GP(batch_op)) * batch);
+  K(t)* lam = (K(t)*)malloc(sizeof(K(t)) * 2 * batch);
+  int cpt = 0, qid = 0;
+#define EXECUTE_AND_RESET() do { GP(batch_add_affine)(R, P, cpt, lam, lam + batch); \
+    for (int u_ = 0; u_ < cpt; u_++) { in_batch[batch_ids[u_]] = 0; } \
+    cpt = 0; } while (0)
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t e = digits[i];
+    if (e == 0 || GP(aff_is_inf)(&points[i])) continue;
+    uint32_t b = e >> 1;
+    const int is_add = (e & 1) == 0;
+    if (is_add) b -= 1;
+    GP(aff) pt = points[i];
+    if (!is_add) K(neg)(&pt.y, &pt.y);
+    if (in_batch[b]) {                       /* conflict: queue it (multiexp_affine.go:179-193) */
+      queue[qid].bucket = b; queue[qid].point = pt; qid++;
+      if (qid == batch - 1) { for (int q = 0; q < qid; q++) GP(add_mixed)(&bucketsJE[queue[q].bucket], &queue[q].point, 0); qid = 0; }
+      continue;
+    }
+    /* add(): special cases without the batch (:108-146) */
+    GP(aff)* BK = &buckets[b];
+    if (GP(aff_is_inf)(BK)) { *BK = pt; continue; }
+    if (K(eq)(&BK->x, &pt.x)) {
+      if (K(eq)(&BK->y, &pt.y)) GP(add_mixed)(&bucketsJE[b], &pt, 0);   /* doubling: rare, other bucket set */
+      else { K(set_zero)(&BK->x); K(set_zero)(&BK->y); }                  /* P + (-P) */
+      continue;
+    }
+    in_batch[b] = 1; batch_ids[cpt] = b; R[cpt] = BK; P[cpt] = pt; cpt++;
+    if (cpt == batch) {
+      EXECUTE_AND_RESET();
+      for (int q = qid - 1; q >= 0; q--) {   /* processTopQueue :155-164 */
+        if (in_batch[queue[q].bucket]) break;
+        GP(aff)* QB = &buckets[queue[q].bucket];
+        GP(aff) qp = queue[q].point;
+        qid--;
+        if (GP(aff_is_inf)(QB)) { *QB = qp; continue; }
+        if (K(eq)(&QB->x, &qp.x)) {
+          if (K(eq)(&QB->y, &qp.y)) GP(add_mixed)(&bucketsJE[queue[q].bucket], &qp, 0);
+          else { K(set_zero)(&QB->x); K(set_zero)(&QB->y); }
+          continue;
+        }
+        in_batch[queue[q].bucket] = 1; batch_ids[cpt] = queue[q].bucket; R[cpt] = QB; P[cpt] = qp; cpt++;
+      }
+    }
+  }
+  EXECUTE_AND_RESET();
+  for (int q = 0; q < qid; q++) GP(add_mixed)(&bucketsJE[queue[q].bucket], &queue[q].point, 0);
+#undef EXECUTE_AND_RESET
+  GP(xyzz) run, tot;
+  GP(xyzz_set_inf)(&run);
+  GP(xyzz_set_inf)(&tot);
+  for (size_t k = nb; k-- > 0;) {            /* :212-221 */
+    GP(add_mixed)(&run, &buckets[k], 0);
+    if (!K(is_zero)(&bucketsJE[k].zz)) GP(xyzz_add)(&run, &bucketsJE[k]);
+    GP(xyzz_add)(&tot, &run);
+  }
+  *total = tot;
+  free(buckets); free(bucketsJE); free(in_batch); free(R); free(P); free(batch_ids); free(queue); free(lam);
+}
+
 /* msmReduceChunk multiexp.go:302-315 */
 static void GP(reduce_chunks)(int c, int W, const GP(xyzz)* totals, GP(xyzz)* out) {
   GP(xyzz) acc = totals[W - 1];
@@ -252,6 +358,7 @@ typedef struct {
   int nleaves;
   /* phase 1: digit tasks (leaf, range); phase 2: window tasks (leaf, window) */
   int phase;
+  int use_batch_affine;
   size_t ntasks;
   size_t next;
   pthread_mutex_t mu;
@@ -273,7 +380,24 @@ static void* GP(worker)(void* arg) {
     } else {
       int j = (int)jb->task_a[t];
       int ce = (j == lf->W - 1) ? GP(last_c)(lf->c) : lf->c;
-      GP(process_chunk)(ce, jb->points + lf->off, lf->digits + (size_t)j * lf->n, lf->n, &lf->totals[j]);
+      const uint32_t* dg = lf->digits + (size_t)j * lf->n;
+      /* getChunkProcessorG1 (multiexp.go:213-299): batch-affine for 10 <= c <= 16 when at least batchSize buckets of the
+       * window are hit (chunkStat.nbBucketFilled, multiexp.go:807-853), extended Jacobian otherwise */
+      int batch = jb->use_batch_affine ? GP(batch_size)(ce) : 0;
+      if (batch) {
+        size_t nbk = (size_t)1 << (ce - 1), filled = 0;
+        unsigned char* seen = (unsigned char*)calloc(nbk, 1);
+        for (size_t i = 0; i < lf->n && filled < (size_t)batch; i++) {
+          uint32_t e = dg[i];
+          if (!e) continue;
+          uint32_t b = (e >> 1) - ((e & 1) ? 0 : 1);
+          if (!seen[b]) { seen[b] = 1; filled++; }
+        }
+        free(seen);
+        if (filled < (size_t)batch) batch = 0;
+      }
+      if (batch) GP(process_chunk_batch_affine)(ce, batch, jb->points + lf->off, dg, lf->n, &lf->totals[j]);
+      else GP(process_chunk)(ce, jb->points + lf->off, dg, lf->n, &lf->totals[j]);
     }
   }
   return NULL;
@@ -316,7 +440,7 @@ static void GP(collect_leaves)(size_t off, size_t n, int nb_tasks, int force_c, 
 
 /* result: affine normal form in out_aff, raw Jacobian (xyzz -> jac of the combined sum) in out_jac */
 static int GP(msm)(const GP(aff)* points, const FR(t)* scalars, size_t n, int force_c, int nthreads, int nb_tasks,
-                   GP(aff)* out_aff, GP(jac)* out_jac, int* used_c, int* used_leaves) {
+                   GP(aff)* out_aff, GP(jac)* out_jac, int* used_c, int* used_leaves, int use_batch_affine) {
   if (nthreads < 1) nthreads = 1;
   if (nb_tasks <= 0) nb_tasks = 2 * nthreads; /* multiexp.go:67-68 with NumCPU := nthreads */
   GP(xyzz) sum;
@@ -334,6 +458,7 @@ static int GP(msm)(const GP(aff)* points, const FR(t)* scalars, size_t n, int fo
     }
     GP(job) jb;
     jb.points = points; jb.scalars = scalars; jb.leaves = leaves; jb.nleaves = nl;
+    jb.use_batch_affine = use_batch_affine;
     pthread_mutex_init(&jb.mu, NULL);
     jb.task_leaf = (size_t*)malloc(sizeof(size_t) * maxtasks);
     jb.task_a = (size_t*)malloc(sizeof(size_t) * maxtasks);
