@@ -25,7 +25,33 @@
 
 namespace gmsm {
 
-#if defined(__CUDA_ARCH__)
+#if defined(GMSM_EMULATE_PTX) && !defined(__CUDACC__)
+// ---- emulated carry-chain primitives (host test build only): PTX semantics of CC.CF, one flag per thread ----
+static thread_local uint32_t emu_cf = 0;
+GMSM_D uint32_t emu_add(uint32_t a, uint32_t b, uint32_t cin, bool set) {
+  uint64_t s = (uint64_t)a + b + cin;
+  if (set) emu_cf = (uint32_t)(s >> 32);
+  return (uint32_t)s;
+}
+GMSM_D uint32_t emu_sub(uint32_t a, uint32_t b, uint32_t bin, bool set) {
+  uint64_t d = (uint64_t)a - b - bin;
+  if (set) emu_cf = (uint32_t)(d >> 32) & 1;
+  return (uint32_t)d;
+}
+GMSM_D uint32_t add_cc(uint32_t a, uint32_t b) { return emu_add(a, b, 0, true); }
+GMSM_D uint32_t addc_cc(uint32_t a, uint32_t b) { return emu_add(a, b, emu_cf, true); }
+GMSM_D uint32_t addc(uint32_t a, uint32_t b) { return emu_add(a, b, emu_cf, false); }
+GMSM_D uint32_t sub_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, 0, true); }
+GMSM_D uint32_t subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, emu_cf, true); }
+GMSM_D uint32_t subc(uint32_t a, uint32_t b) { return emu_sub(a, b, emu_cf, false); }
+GMSM_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add((uint32_t)((uint64_t)a * b), c, 0, true); }
+GMSM_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add((uint32_t)((uint64_t)a * b), c, emu_cf, true); }
+GMSM_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add((uint32_t)(((uint64_t)a * b) >> 32), c, emu_cf, true); }
+GMSM_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add((uint32_t)(((uint64_t)a * b) >> 32), c, emu_cf, false); }
+// a dropped carry-out must be zero: checked in the emulated build, free on the device
+#define GMSM_NO_CARRY() do { if (emu_cf) __builtin_trap(); } while (0)
+#elif defined(__CUDA_ARCH__)
+#define GMSM_NO_CARRY() do { } while (0)
 // ---- PTX carry-chain primitives (CC.CF lives across consecutive volatile asm statements) ----
 GMSM_D uint32_t add_cc(uint32_t a, uint32_t b) {
   uint32_t r;
@@ -72,6 +98,11 @@ GMSM_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
   asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
+GMSM_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 #endif
 
 template <class P>
@@ -112,7 +143,7 @@ template <class P>
 GMSM_HD void fp_reduce_once(Fp<P>& a) {
   constexpr int N = P::N;
   uint32_t t[N];
-#if defined(__CUDA_ARCH__)
+#if defined(GMSM_PTX_PATH)
   t[0] = sub_cc(a.l[0], P::mod(0));
 #pragma unroll
   for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::mod(i));
@@ -136,7 +167,7 @@ template <class P>
 GMSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   Fp<P> r;
-#if defined(__CUDA_ARCH__)
+#if defined(GMSM_PTX_PATH)
   r.l[0] = add_cc(a.l[0], b.l[0]);
 #pragma unroll
   for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
@@ -164,7 +195,7 @@ template <class P>
 GMSM_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   Fp<P> r;
-#if defined(__CUDA_ARCH__)
+#if defined(GMSM_PTX_PATH)
   r.l[0] = sub_cc(a.l[0], b.l[0]);
 #pragma unroll
   for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
@@ -205,7 +236,7 @@ template <class P>
 GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   constexpr int N = P::N;
   Fp<P> r;
-#if defined(__CUDA_ARCH__) && !defined(GMSM_PORTABLE_MUL)
+#if defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
   // Two accumulators, N+2 slots each: [0..N-1] limbs, [N] carry limb, [N+1] always zero.
   uint32_t A[N + 2], B[N + 2];
 #pragma unroll

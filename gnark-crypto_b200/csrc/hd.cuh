@@ -8,3 +8,10 @@
 #define GMSM_HD inline __attribute__((always_inline))
 #define GMSM_D inline __attribute__((always_inline))
 #endif
+
+// GMSM_PTX_PATH selects the carry-chain formulation of the field arithmetic (field.cuh): on the device it is inline PTX;
+// with -DGMSM_EMULATE_PTX a host build runs the SAME source over emulated primitives (one carry flag per thread), so the
+// exact limb/carry schedule that ptxas sees is checked on a CPU by tests/test_hostcheck.py.
+#if defined(__CUDA_ARCH__) || (defined(GMSM_EMULATE_PTX) && !defined(__CUDACC__))
+#define GMSM_PTX_PATH 1
+#endif

@@ -17,14 +17,44 @@ static int run(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t
   return 0;
 }
 
+// -DHC_GROUP=k compiles one group per translation unit (hostcheck_op_k) so the test can build the six in parallel;
+// without it this file is the dispatcher + the window plan.
+#if defined(HC_GROUP)
+#define HC_CAT2(a, b) a##b
+#define HC_CAT(a, b) HC_CAT2(a, b)
+#if HC_GROUP == 0
+using HcG = bn254_g1;
+#elif HC_GROUP == 1
+using HcG = bn254_g2;
+#elif HC_GROUP == 2
+using HcG = bls12381_g1;
+#elif HC_GROUP == 3
+using HcG = bls12381_g2;
+#elif HC_GROUP == 4
+using HcG = bls12377_g1;
+#else
+using HcG = bls12377_g2;
+#endif
+extern "C" int HC_CAT(hostcheck_op_, HC_GROUP)(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
+  return run<HcG>(op, a, b, o, n);
+}
+#else
+extern "C" {
+int hostcheck_op_0(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_op_1(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_op_2(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_op_3(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_op_4(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_op_5(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+}
 extern "C" int hostcheck_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   switch (curve) {
-    case 0: return run<bn254_g1>(op, a, b, o, n);
-    case 1: return run<bn254_g2>(op, a, b, o, n);
-    case 2: return run<bls12381_g1>(op, a, b, o, n);
-    case 3: return run<bls12381_g2>(op, a, b, o, n);
-    case 4: return run<bls12377_g1>(op, a, b, o, n);
-    case 5: return run<bls12377_g2>(op, a, b, o, n);
+    case 0: return hostcheck_op_0(op, a, b, o, n);
+    case 1: return hostcheck_op_1(op, a, b, o, n);
+    case 2: return hostcheck_op_2(op, a, b, o, n);
+    case 3: return hostcheck_op_3(op, a, b, o, n);
+    case 4: return hostcheck_op_4(op, a, b, o, n);
+    case 5: return hostcheck_op_5(op, a, b, o, n);
   }
   return 1;
 }
@@ -33,3 +63,4 @@ extern "C" void hostcheck_plan(int fr_bits, int c, int* out6) {
   WindowPlan p = make_plan(fr_bits, c);
   out6[0] = p.c; out6[1] = p.nwin; out6[2] = p.last_c; out6[3] = (int)p.nb; out6[4] = (int)p.nb_last; out6[5] = (int)p.nb_total;
 }
+#endif

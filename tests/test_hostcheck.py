@@ -1,6 +1,7 @@
-"""CPU build (g++, portable arithmetic path) of the product's field / curve headers against the
-oracle: checks the formulas and the window plan without a GPU.  The device (PTX) arithmetic path is
-checked by the same vectors in tests/test_gpu_ops.py."""
+"""CPU builds (g++) of the product's field / curve headers against the oracle, without a GPU, in two variants:
+"portable" = the plain C++ arithmetic path; "emulated" = the device's carry-chain formulation (the source ptxas sees,
+-DGMSM_EMULATE_PTX: mad.lo.cc / madc.hi.cc / addc ... over an emulated carry flag, dropped carries trap).  The PTX itself
+is checked by the same vectors on the GPU in tests/test_gpu_ops.py."""
 import ctypes
 import os
 import subprocess
@@ -13,14 +14,35 @@ from tests import opcases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "gnark-crypto_b200", "csrc")
-OUT = os.path.join(ROOT, "gnark-crypto_b200", "build", "libgmsm_hostcheck.so")
+OUT = os.path.join(ROOT, "gnark-crypto_b200", "build", "libgmsm_hostcheck%s.so")
+_LIBS = {}
 
 
-@pytest.fixture(scope="module")
-def hc():
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", OUT, os.path.join(CSRC, "hostcheck.cpp")], check=True)
-    return ctypes.CDLL(OUT)
+def _build(variant):
+    """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
+    if variant not in _LIBS:
+        tag = "" if variant == "portable" else "_emu"
+        out = OUT % tag
+        bdir = os.path.dirname(out)
+        os.makedirs(bdir, exist_ok=True)
+        srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h", ".cpp"))]
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in srcs):
+            flags = ["-std=c++17", "-O1", "-fPIC"] + ([] if variant == "portable" else ["-DGMSM_EMULATE_PTX"])
+            src = os.path.join(CSRC, "hostcheck.cpp")
+            objs, procs = [], []
+            for k in list(range(6)) + [None]:
+                o = os.path.join(bdir, "hostcheck%s_%s.o" % (tag, "d" if k is None else k))
+                objs.append(o)
+                procs.append(subprocess.Popen(["g++", *flags, *([] if k is None else ["-DHC_GROUP=%d" % k]), "-c", "-o", o, src]))
+            assert all(p.wait() == 0 for p in procs)
+            subprocess.run(["g++", "-shared", "-o", out, *objs], check=True)
+        _LIBS[variant] = ctypes.CDLL(out)
+    return _LIBS[variant]
+
+
+@pytest.fixture(scope="module", params=["portable", "emulated"])
+def hc(request):
+    return _build(request.param)
 
 
 def _runner(hc, g):
@@ -59,3 +81,34 @@ def test_window_plan(hc):
             W = O.compute_nb_chunks(bits, c)
             lc = O.last_c(bits, c)
             assert list(buf) == [c, W, lc, 1 << (c - 1), 1 << (lc - 1), (W - 1) * (1 << (c - 1)) + (1 << (lc - 1))]
+
+
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1"])
+def test_carry_chain_mul_sqr_stress(g):
+    """the device formulation of Mul / Square (emulated) against the portable path and big-int arithmetic on many random
+    and extreme operands (limbs of all-ones, single bits, q-1, values next to the limb boundaries)"""
+    G = O.GROUPS[g]
+    f = G.K.f
+    rng = np.random.default_rng(17)
+    nl = f.limbs * 2
+    import random
+    r = random.Random(5)
+    vals = [0, 1, 2, f.q - 1, f.q - 2, f.Rmod, f.R2, (f.q - 1) // 2, (f.q + 1) // 2]
+    for k in range(0, 32 * nl, 7):
+        vals += [(1 << k) % f.q, ((1 << k) - 1) % f.q, (f.q - (1 << k)) % f.q]
+    top = (1 << (32 * nl)) - 1
+    for k in range(nl):
+        vals.append((top ^ (0xFFFFFFFF << (32 * k))) % f.q)
+        vals.append((0xFFFFFFFF << (32 * k)) % f.q)
+    vals += [r.randrange(f.q) for _ in range(3000)]
+    A = np.array([f.to_limbs(v) for v in vals], dtype=np.uint64).view(np.uint32).reshape(len(vals), nl)
+    perm = rng.permutation(len(vals))
+    B = A[perm]
+    run_p, run_e = _runner(_build("portable"), g), _runner(_build("emulated"), g)
+    mp, me = run_p(0, A, B, nl), run_e(0, A, B, nl)
+    sp, se = run_p(3, A, None, nl), run_e(3, A, None, nl)
+    assert np.array_equal(mp, me) and np.array_equal(sp, se)
+    got_m = [f.from_limbs(row) for row in me.view(np.uint64)]
+    got_s = [f.from_limbs(row) for row in se.view(np.uint64)]
+    assert got_m == [vals[i] * vals[perm[i]] * f.Rinv % f.q for i in range(len(vals))]
+    assert got_s == [v * v * f.Rinv % f.q for v in vals]
