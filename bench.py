@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--sample-logn", type=int, default=0, help="cpu baseline sample size (log2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tables", action="store_true", help="skip the window-table (precomputed resident bases) measurement")
+    ap.add_argument("--table-c", type=int, default=0, help="window width of the table mode (0 = engine model)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,6 +313,39 @@ def main():
         "clocks": clocks,
     }
 
+    # ---- window tables for resident bases (gmsm_bases_precompute): the static-SRS flow.  NOT the headline: the
+    # headline `value` is the plain MultiExp whose bases may change on every call, like the reference's. ----
+    if world == 1 and not args.no_tables:
+        teng = pkg.Engine(g, n, c=args.table_c, device=local_rank, tables=True)
+        t0 = time.perf_counter()
+        d_table = teng.build_tables(d_points, n)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        teng.set_profiling(True)
+        for _ in range(max(args.warmup, 3)):
+            tout = teng.msm_tables(d_table, n, d_scalars, n)
+        torch.cuda.synchronize()
+        tev0, tev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tev0.record()
+        for _ in range(args.steps):
+            tout = teng.msm_tables(d_table, n, d_scalars, n)
+        tev1.record()
+        torch.cuda.synchronize()
+        t_ms = tev0.elapsed_time(tev1) / args.steps
+        if not np.array_equal(tout.cpu().numpy().view(np.uint64), result_jac):
+            raise SystemExit("bench.py: window-table result differs from the plain result")
+        tst = teng.last_stage_ms()
+        line["resident_tables"] = {
+            "value": n / (t_ms * 1e-3), "unit": "scalar-muls/s", "ms_per_step": t_ms, "c": teng.c, "windows": teng.nwin,
+            "table_bytes": int(d_table.numel()) * 8, "table_build_s": build_s,
+            "stages_ms": dict(zip(stage_names, [float(x) for x in tst])),
+            "accumulate_alg_GBps": n * teng.nwin * (A + 2) / (tst[3] * 1e-3) / 1e9,
+            "note": "bases precomputed once as W rows 2^(c*j)*P (one shared bucket set, no Horner); result bit-identical to `value`'s",
+        }
+        line["gpu_launches"] += teng.last_launches * args.steps
+        teng.close()
+        del d_table
+
     # ---- end to end through the reference-facing call, host buffers ----
     if not args.no_e2e:
         h_points = torch.empty(n * wds, dtype=torch.int64).pin_memory()
@@ -362,11 +397,22 @@ def main():
             for _ in range(args.steps):
                 rr = rb.MultiExp(hs.reshape(n, 4))
             dtr = (time.perf_counter() - t0) / args.steps
-            rb.close()
             if not np.array_equal(rr, result_jac):
                 raise SystemExit("bench.py: resident-bases result differs")
             line["e2e_resident_bases"] = {"value": n / dtr, "unit": "scalar-muls/s", "ms_per_step": dtr * 1e3,
                                           "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": jac_words * 8}
+            if not args.no_tables:
+                tc = rb.Precompute(args.table_c)
+                rb.MultiExp(hs.reshape(n, 4))
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    rr = rb.MultiExp(hs.reshape(n, 4))
+                dtt = (time.perf_counter() - t0) / args.steps
+                if not np.array_equal(rr, result_jac):
+                    raise SystemExit("bench.py: resident-bases (window tables) result differs")
+                line["e2e_resident_tables"] = {"value": n / dtt, "unit": "scalar-muls/s", "ms_per_step": dtt * 1e3, "c": tc,
+                                               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": jac_words * 8}
+            rb.close()
         del h_points, h_scal
 
     # ---- CPU baseline: the oracle's C port on a bounded sample (rank 0, N = 1 only) + parity on it ----

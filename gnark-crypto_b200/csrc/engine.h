@@ -37,6 +37,12 @@ struct gmsm_ctx {
   size_t max_n = 0;
   gmsm::CurveInfo ci{};
   gmsm::WindowPlan plan{};
+  // window-table mode (gmsm_ctx_create_tables): the point operand is a table of W rows, row j = 2^(c*j) * bases,
+  // all windows share one bucket set of plan.nb_total = max(nb, nb_last) buckets, the bucket reduction and the
+  // finalize see a single window.  tab_stride = points per table row (set by the caller before each accumulate).
+  bool shared = false;
+  uint32_t tab_stride = 0;
+  int red_windows() const { return shared ? 1 : plan.nwin; }   // partials per call
   // chunking
   uint32_t K2 = 16;
   uint32_t seg_L = 32, seg_S = 0;
@@ -111,6 +117,7 @@ struct GroupVTable {
   int (*test_op)(int op, const uint32_t* da, const uint32_t* db, uint32_t* dout, size_t n);
   int (*digits_dump)(const void* d_scalars, size_t n, int c, int nwin, uint32_t* dout);
   int (*batch_scalar_mul)(const void* d_table, const void* d_scalars, size_t n, int c, int nwin, void* d_out, cudaStream_t);
+  int (*table_level)(const void* d_in, size_t n, int c, void* d_out, cudaStream_t);   // out[i] = 2^c * in[i]
 };
 extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1, vt_bls12377_g2;
 

@@ -38,7 +38,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, p.nb, c->digits, c->hist);
+    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->hist);
     launches++;
     LAUNCH_CHECK();
   }
@@ -60,8 +60,30 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   // and run underneath the first part of the accumulate kernel (multiplier-bound, L2 idle) -- see K2.
   // (measured: -1.3 ms at bn254 G1 2^24, -0.5 ms bls12-381 G1; +0.8 ms for G2, whose 255-register accumulate
   // blocks leave no room for co-resident scatter blocks -> G1 groups only)
+  // Window-table mode: one pass per bucket range instead of one per window (k_scatter_shared); the ranges play
+  // the role of the windows for the overlap with the accumulate.
+  const int NPASS = p.nwin;
+  const uint32_t range_sz = c->shared ? (p.nb_total + (uint32_t)NPASS - 1) / (uint32_t)NPASS : p.nb;
   const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->split_w, p.nwin) : p.nwin;
-  {
+  if (c->shared) {
+    unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 2u);
+    auto scatter = [&](int r, cudaStream_t s) {
+      const uint32_t blo = std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
+      const uint32_t bhi = std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
+      if (blo >= bhi) return;
+      k_scatter_shared<<<dim3(blocks, (unsigned)p.nwin), 256, 0, s>>>(c->digits, n32, c->tab_stride, c->hist, c->offsets,
+                                                                       c->entries, blo, bhi);
+      launches++;
+    };
+    if (SPLIT_W < NPASS) {
+      CK(cudaEventRecord(c->ev_split[0], st));
+      CK(cudaStreamWaitEvent(c->aux, c->ev_split[0], 0));
+      for (int r = SPLIT_W; r < NPASS; r++) scatter(r, c->aux);
+      CK(cudaEventRecord(c->ev_split[1], c->aux));
+    }
+    for (int r = 0; r < SPLIT_W; r++) scatter(r, st);
+    LAUNCH_CHECK();
+  } else {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 8u);
     auto scatter = [&](int j, cudaStream_t s) {
       k_scatter_window<<<blocks, 256, 0, s>>>(c->digits + (size_t)j * n, n32, c->hist + (size_t)j * p.nb,
@@ -78,6 +100,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
     LAUNCH_CHECK();
   }
   mark(3);
+  if (c->affine && c->shared) return set_err(GMSM_EINVAL, "internal: window tables need the default accumulation mode");
   if (c->affine && rmw) return set_err(GMSM_EINVAL, "internal: batch-affine accumulation cannot extend existing buckets");
   if (c->affine) {
     // K2 (batch-affine): balanced tree over the bucket-ordered entries, one shared inversion per level
@@ -149,7 +172,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
     {
       X* carr = reinterpret_cast<X*>(c->carries[0]);
       if (SPLIT_W < p.nwin) {
-        const uint32_t split_bucket = (uint32_t)SPLIT_W * p.nb;
+        const uint32_t split_bucket = (uint32_t)std::min<uint64_t>((uint64_t)SPLIT_W * range_sz, p.nb_total);
         k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
                                                             buckets, carr, c->carry_ids[0], 1, split_bucket);
         CK(cudaStreamWaitEvent(st, c->ev_split[1], 0));   // the remaining windows are scattered
@@ -202,8 +225,11 @@ static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
   X* buckets = reinterpret_cast<X*>(c->buckets);
   {
     const uint32_t S = c->seg_S, L = c->seg_L;
-    k_bucket_segments<G><<<nblk((size_t)p.nwin * S, 128), 128, 0, st>>>(buckets, p.nwin, p.nb, p.nb_last, L, S,
-                                                                       reinterpret_cast<X*>(c->seg[0]));
+    // window-table mode: one window of nb_total shared buckets
+    const int nwin = c->red_windows();
+    const uint32_t nb_reg = c->shared ? p.nb_total : p.nb, nb_last = c->shared ? p.nb_total : p.nb_last;
+    k_bucket_segments<G><<<nblk((size_t)nwin * S, 128), 128, 0, st>>>(buckets, nwin, nb_reg, nb_last, L, S,
+                                                                     reinterpret_cast<X*>(c->seg[0]));
     launches++;
     LAUNCH_CHECK();
     uint32_t per = S;
@@ -212,15 +238,15 @@ static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
       uint32_t R = 16;
       uint32_t outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? reinterpret_cast<X*>(d_partials) : reinterpret_cast<X*>(c->seg[cur ^ 1]);
-      k_sum_groups<G><<<nblk((size_t)p.nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
-                                                                       p.nwin, dst);
+      k_sum_groups<G><<<nblk((size_t)nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
+                                                                     nwin, dst);
       launches++;
       LAUNCH_CHECK();
       per = outp;
       cur ^= 1;
     }
     if (S == 1) {
-      CK(cudaMemcpyAsync(d_partials, c->seg[0], (size_t)p.nwin * sizeof(X), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(d_partials, c->seg[0], (size_t)nwin * sizeof(X), cudaMemcpyDeviceToDevice, st));
     }
   }
   mark(6);
@@ -239,7 +265,7 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
 template <class G>
 static int run_finalize(gmsm_ctx* c, const void* d_partials, int nranks, void* d_out, cudaStream_t st) {
   using F = typename G::F;
-  k_finalize<G><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->plan.nwin, c->plan.c,
+  k_finalize<G><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
                                   reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
   LAUNCH_CHECK();
   return GMSM_OK;
@@ -279,8 +305,17 @@ static int run_batch_scalar_mul(const void* d_table, const void* d_scalars, size
   return GMSM_OK;
 }
 
+template <class G>
+static int run_table_level(const void* d_in, size_t n, int c, void* d_out, cudaStream_t st) {
+  using A = Affine<typename G::F>;
+  k_table_level<G><<<nblk((n + TAB_M - 1) / TAB_M, 128), 128, 0, st>>>(reinterpret_cast<const A*>(d_in), (uint32_t)n, c,
+                                                                       reinterpret_cast<A*>(d_out));
+  LAUNCH_CHECK();
+  return GMSM_OK;
+}
+
 #define GMSM_INSTANTIATE(G, NAME)                                                                  \
   const GroupVTable NAME = {&run_window_sums<G>, &run_accumulate<G>, &run_bucket_reduce<G>, &run_finalize<G>, &run_generate<G>, &test_op_sizes<G>, \
-                            &run_test_op<G>, &run_digits_dump<G>, &run_batch_scalar_mul<G>};
+                            &run_test_op<G>, &run_digits_dump<G>, &run_batch_scalar_mul<G>, &run_table_level<G>};
 
 }  // namespace gmsm

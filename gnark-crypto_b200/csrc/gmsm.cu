@@ -101,6 +101,24 @@ static int choose_c(int fr_bits, size_t n) {
   return bc;
 }
 
+// window width of the window-table mode: one shared bucket set, so the bucket reduction costs 2^(c-1) * ~3.8
+// full-add equivalents ONCE instead of per window, and c can grow until that term meets the W(c)*n accumulate
+// term: c = 22 (W = 12) at n = 2^24 for the 253..255-bit scalar fields.  GMSM_TABLE_C forces it.
+static int choose_c_tables(int fr_bits, size_t n) {
+  if (const char* e = getenv("GMSM_TABLE_C")) {
+    int c = atoi(e);
+    if (c >= 2 && c <= 24) return c;
+  }
+  double best = 1e300;
+  int bc = 8;
+  for (int c = 6; c <= 24; c++) {
+    WindowPlan p = make_plan(fr_bits, c);
+    double cost = (double)p.nwin * (double)n + (double)std::max(p.nb, p.nb_last) * 3.8 * 1.4;
+    if (cost < best) { best = cost; bc = c; }
+  }
+  return bc;
+}
+
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
@@ -128,8 +146,8 @@ static int ctx_alloc(gmsm_ctx* c) {
   c->seg_L = 32;  // buckets per reduction segment (GMSM_SEG_L to experiment)
   if (const char* e = getenv("GMSM_SEG_L")) { int v = atoi(e); if (v >= 2 && v <= 1024) c->seg_L = (uint32_t)v; }
   c->seg_S = (nbmax + c->seg_L - 1) / c->seg_L;
-  CK(dmalloc(&c->seg[0], (size_t)p.nwin * c->seg_S * xyzz, &acc));
-  CK(dmalloc(&c->seg[1], (size_t)p.nwin * ((c->seg_S + 15) / 16) * xyzz, &acc));
+  CK(dmalloc(&c->seg[0], (size_t)c->red_windows() * c->seg_S * xyzz, &acc));
+  CK(dmalloc(&c->seg[1], (size_t)c->red_windows() * ((c->seg_S + 15) / 16) * xyzz, &acc));
   if (c->affine) {
     const size_t aff = 8u * c->ci.coord_words, fe = 4u * c->ci.coord_words;
     const size_t m1 = (ent + std::min(nbp, ent)) / 2 + 2, m2 = (m1 + std::min(nbp, m1)) / 2 + 2;
@@ -170,7 +188,15 @@ static void ctx_free(gmsm_ctx* c) {
   if (c->aux) cudaStreamDestroy(c->aux);
 }
 
+static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int device, bool shared);
 extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, int device) {
+  return ctx_create_ex(curve, max_n, c, device, false);
+}
+extern "C" gmsm_ctx_t* gmsm_ctx_create_tables(gmsm_curve_t curve, size_t max_n, int c, int device) {
+  return ctx_create_ex(curve, max_n, c, device, true);
+}
+
+static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int device, bool shared) {
   CurveInfo ci;
   if (!curve_info(curve, &ci)) { set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve); return nullptr; }
   if (c != 0 && (c < 2 || c > 24)) { set_err(GMSM_EINVAL, "window width c=%d out of range [2,24]", c); return nullptr; }
@@ -187,14 +213,17 @@ extern "C" gmsm_ctx_t* gmsm_ctx_create(gmsm_curve_t curve, size_t max_n, int c, 
   ctx->device = device;
   ctx->max_n = max_n;
   ctx->ci = ci;
-  if (c == 0) c = choose_c(ci.fr_bits, max_n);
+  if (c == 0) c = shared ? choose_c_tables(ci.fr_bits, max_n) : choose_c(ci.fr_bits, max_n);
+  ctx->shared = shared;
   // bucket accumulation: extended-Jacobian segmented reduction by default (INT-multiplier bound at 89 % of the
   // pipe); GMSM_AFFINE=1 selects the batch-affine tree (fewer multiplies, but 3x the HBM traffic: measured
   // 46.3 ms vs 42.1 ms at bn254 G1 n=2^24, profiles/r01_ncu_affine_*).
   ctx->affine = false;
   if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
+  if (shared) ctx->affine = false;   // the window-table mode has one accumulation path
   if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = v; }
   ctx->plan = make_plan(ci.fr_bits, c);
+  if (shared) ctx->plan.nb_total = std::max(ctx->plan.nb, ctx->plan.nb_last);   // one bucket set for all windows
   if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
     set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 32-bit entry index; shard the MSM", max_n, ctx->plan.nwin);
     delete ctx;
@@ -231,6 +260,7 @@ extern "C" int gmsm_ctx_last_stage_ms(gmsm_ctx_t* ctx, float out_ms[8]) {
 extern "C" int gmsm_ctx_window_sums_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
                                            void* d_partials, void* stream) {
   if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (ctx->shared) return set_err(GMSM_EINVAL, "window-table context: use gmsm_ctx_msm_tables_device");
   if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
   std::lock_guard<std::mutex> lk(ctx->mu);
   CK(cudaSetDevice(ctx->device));
@@ -258,12 +288,59 @@ extern "C" int gmsm_ctx_finalize_device(gmsm_ctx_t* ctx, const void* d_partials,
 extern "C" int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
                                    void* d_out_jac, void* stream) {
   if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (ctx->shared) return set_err(GMSM_EINVAL, "window-table context: use gmsm_ctx_msm_tables_device");
   if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
   std::lock_guard<std::mutex> lk(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   int rc = GMSM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   rc = vtable(ctx->curve)->window_sums(ctx, d_points, d_scalars, n, ctx->win_partials, st);
+  if (rc != GMSM_OK) return rc;
+  rc = vtable(ctx->curve)->finalize(ctx, ctx->win_partials, 1, d_out_jac, st);
+  if (rc != GMSM_OK) return rc;
+  ctx->last_launches += 1;
+  if (ctx->profiling) {
+    cudaEventRecord(ctx->ev[7], st);
+    cudaEventRecord(ctx->ev[8], st);
+    ctx->have_stage = true;
+  }
+  return GMSM_OK;
+}
+
+// ---- window tables (device level) ----
+extern "C" int gmsm_tables_build_device(gmsm_curve_t curve, int c, const void* d_points, size_t n, void* d_table,
+                                        size_t row_stride, void* stream) {
+  CurveInfo ci;
+  if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
+  if (c < 2 || c > 24) return set_err(GMSM_EINVAL, "window width c=%d out of range [2,24]", c);
+  if (row_stride < n) return set_err(GMSM_EINVAL, "row_stride %zu < n %zu", row_stride, n);
+  const WindowPlan p = make_plan(ci.fr_bits, c);
+  if ((double)row_stride * p.nwin >= 2147483000.0)
+    return set_err(GMSM_EINVAL, "row_stride*W = %zu*%d does not fit the 31-bit table index; shard the bases", row_stride, p.nwin);
+  if (n == 0) return GMSM_OK;
+  const size_t ab = 8u * ci.coord_words;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_table != d_points) CK(cudaMemcpyAsync(d_table, d_points, n * ab, cudaMemcpyDeviceToDevice, st));
+  for (int j = 1; j < p.nwin; j++) {
+    if (int rc = vtable(curve)->table_level((const char*)d_table + (size_t)(j - 1) * row_stride * ab, n, c,
+                                            (char*)d_table + (size_t)j * row_stride * ab, st)) return rc;
+  }
+  return GMSM_OK;
+}
+
+extern "C" int gmsm_ctx_msm_tables_device(gmsm_ctx_t* ctx, const void* d_table, size_t row_stride, size_t offset,
+                                          const void* d_scalars, size_t n, void* d_out_jac, void* stream) {
+  if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
+  if (!ctx->shared) return set_err(GMSM_EINVAL, "context was not created with gmsm_ctx_create_tables");
+  if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
+  if (offset > row_stride || n > row_stride - offset) return set_err(GMSM_EINVAL, "len(points) != len(scalars)");
+  if ((double)row_stride * ctx->plan.nwin >= 2147483000.0) return set_err(GMSM_EINVAL, "row_stride*W does not fit the 31-bit table index");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->tab_stride = (uint32_t)row_stride;
+  const size_t ab = 8u * ctx->ci.coord_words;
+  int rc = vtable(ctx->curve)->window_sums(ctx, (const char*)d_table + offset * ab, d_scalars, n, ctx->win_partials, st);
   if (rc != GMSM_OK) return rc;
   rc = vtable(ctx->curve)->finalize(ctx, ctx->win_partials, 1, d_out_jac, st);
   if (rc != GMSM_OK) return rc;
@@ -293,6 +370,10 @@ struct Pipeline {
   cudaStream_t copy_st = nullptr, comp_st = nullptr;
   cudaEvent_t ev[16] = {};
   int last_launches = 0;
+  // window-table mode (gmsm_bases_precompute): d_points of pipeline_run is then the table, row stride tab_stride
+  bool tables = false;
+  size_t tab_stride = 0;
+  int tab_c = 0;
 };
 
 static int pipeline_init(Pipeline& P, int curve, int device) {
@@ -344,16 +425,18 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     P.scal_cap = n;
   }
   // window width from the TOTAL size (all batches share one bucket array); workspace sized for one batch
-  const int c = c_force ? c_force : choose_c(ci.fr_bits, n);
-  if (!P.ctx || P.ctx->max_n < nc || P.ctx->max_n > 4 * nc + 1024 || P.ctx->plan.c != c) {
+  const int c = P.tables ? P.tab_c : (c_force ? c_force : choose_c(ci.fr_bits, n));
+  if (!P.ctx || P.ctx->max_n < nc || P.ctx->max_n > 4 * nc + 1024 || P.ctx->plan.c != c || P.ctx->shared != P.tables) {
     if (P.ctx) { gmsm_ctx_destroy(P.ctx); P.ctx = nullptr; }
-    P.ctx = gmsm_ctx_create((gmsm_curve_t)P.curve, nc, c, P.device);
+    P.ctx = ctx_create_ex((gmsm_curve_t)P.curve, nc, c, P.device, P.tables);
     if (!P.ctx) return GMSM_ECUDA;
   }
-  if (P.partials_cap < nch * P.ctx->plan.nwin) {
+  P.ctx->tab_stride = (uint32_t)P.tab_stride;
+  const int npart = P.ctx->red_windows();   // partials per batch / per call: W, or 1 in window-table mode
+  if (P.partials_cap < nch * npart) {
     cudaFree(P.d_partials); P.d_partials = nullptr;
-    CK(cudaMalloc(&P.d_partials, (size_t)nch * P.ctx->plan.nwin * xb));
-    P.partials_cap = nch * P.ctx->plan.nwin;
+    CK(cudaMalloc(&P.d_partials, (size_t)nch * npart * xb));
+    P.partials_cap = nch * npart;
   }
   const GroupVTable* vt = vtable(P.curve);
   const char* hp = reinterpret_cast<const char*>(h_points);
@@ -378,7 +461,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
       rc = vt->accumulate(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m, k > 0, P.comp_st);
     } else {
       rc = vt->window_sums(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m,
-                           (char*)P.d_partials + (size_t)k * P.ctx->plan.nwin * xb, P.comp_st);
+                           (char*)P.d_partials + (size_t)k * npart * xb, P.comp_st);
     }
     if (rc) return rc;
     launches += P.ctx->last_launches;
@@ -388,7 +471,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     if (int rc = vt->bucket_reduce(P.ctx, P.d_partials, P.comp_st)) return rc;
     launches += P.ctx->last_launches;
     if (h_partials) {
-      CK(cudaMemcpyAsync(h_partials, P.d_partials, (size_t)P.ctx->plan.nwin * xb, cudaMemcpyDeviceToHost, P.comp_st));
+      CK(cudaMemcpyAsync(h_partials, P.d_partials, (size_t)npart * xb, cudaMemcpyDeviceToHost, P.comp_st));
       CK(cudaStreamSynchronize(P.comp_st));
       CK(cudaStreamSynchronize(P.copy_st));
       P.last_launches = launches;
@@ -511,6 +594,49 @@ extern "C" gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* p
   return b;
 }
 
+// Window tables for resident bases: every shard's point array is replaced by its W-row table (row 0 = the bases,
+// row j = 2^(c*j) * bases; W x the memory), built once on the device; later gmsm_bases_multiexp calls run the
+// single-bucket-set pass with c ~ 22 (W = 12) instead of c = 17 (W = 15).  Results are bit-identical.
+extern "C" int gmsm_bases_precompute(gmsm_bases_t* b, int c) {
+  if (!b) return set_err(GMSM_EINVAL, "null bases");
+  if (c != 0 && (c < 2 || c > 24)) return set_err(GMSM_EINVAL, "window width c=%d out of range [2,24]", c);
+  std::lock_guard<std::mutex> lk(b->mu);
+  CurveInfo ci;
+  curve_info(b->curve, &ci);
+  const size_t ab = 8u * ci.coord_words;
+  size_t max_sh = 0;
+  for (BaseShard& sh : b->shards) {
+    if (sh.pipe.tables) return set_err(GMSM_EINVAL, "window tables already built (c=%d)", sh.pipe.tab_c);
+    max_sh = std::max(max_sh, sh.hi - sh.lo);
+  }
+  if (c == 0) c = choose_c_tables(ci.fr_bits, std::max<size_t>(max_sh, 1));
+  const WindowPlan p = make_plan(ci.fr_bits, c);
+  if ((double)max_sh * p.nwin >= 2147483000.0)
+    return set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 31-bit table index; shard the bases", max_sh, p.nwin);
+  for (BaseShard& sh : b->shards) {
+    const size_t m = sh.hi - sh.lo;
+    CK(cudaSetDevice(sh.device));
+    void* tab = nullptr;
+    const size_t bytes = m * (size_t)p.nwin * ab;
+    cudaError_t e = cudaMalloc(&tab, bytes ? bytes : 16);
+    if (e != cudaSuccess) return set_err(GMSM_ENOMEM, "window tables: %zu bytes on device %d: %s", bytes, sh.device, cudaGetErrorString(e));
+    int rc = gmsm_tables_build_device((gmsm_curve_t)b->curve, c, sh.d_points, m, tab, m, sh.pipe.comp_st);
+    if (rc == GMSM_OK) {
+      e = cudaStreamSynchronize(sh.pipe.comp_st);
+      if (e != cudaSuccess) rc = set_err(GMSM_ECUDA, "window tables: %s", cudaGetErrorString(e));
+    }
+    if (rc != GMSM_OK) { cudaFree(tab); return rc; }
+    cudaFree(sh.d_points);
+    sh.d_points = tab;
+    sh.pipe.tables = true;
+    sh.pipe.tab_stride = m;
+    sh.pipe.tab_c = c;
+  }
+  return GMSM_OK;
+}
+/* window width / number of table rows of precomputed bases (0 if none) */
+extern "C" int gmsm_bases_table_bits(const gmsm_bases_t* b) { return (b && !b->shards.empty() && b->shards[0].pipe.tables) ? b->shards[0].pipe.tab_c : 0; }
+
 extern "C" void gmsm_bases_free(gmsm_bases_t* b) {
   if (!b) return;
   for (BaseShard& sh : b->shards) {
@@ -543,9 +669,12 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
     BaseShard& sh = *jobs[0].sh;
     return pipeline_run(sh.pipe, reinterpret_cast<char*>(sh.d_points) + (jobs[0].a - sh.lo) * ab, nullptr, scalars, n, out_jac);
   }
-  const int c = choose_c(ci.fr_bits, n);
+  // window-table mode: every shard carries the same table width and returns ONE partial
+  const bool tables = jobs[0].sh->pipe.tables;
+  const int c = tables ? jobs[0].sh->pipe.tab_c : choose_c(ci.fr_bits, n);
   const WindowPlan plan = make_plan(ci.fr_bits, c);
-  std::vector<unsigned char> h_part(jobs.size() * plan.nwin * xb);
+  const size_t npart = tables ? 1 : (size_t)plan.nwin;
+  std::vector<unsigned char> h_part(jobs.size() * npart * xb);
   std::vector<int> rcs(jobs.size(), GMSM_OK);
   std::vector<std::string> errs(jobs.size());
   {
@@ -554,7 +683,7 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
       th.emplace_back([&, k]() {
         const Job& j = jobs[k];
         rcs[k] = pipeline_run(j.sh->pipe, reinterpret_cast<char*>(j.sh->d_points) + (j.a - j.sh->lo) * ab, nullptr,
-                              scalars + (j.a - offset) * 4, j.e - j.a, nullptr, c, h_part.data() + k * plan.nwin * xb);
+                              scalars + (j.a - offset) * 4, j.e - j.a, nullptr, c, h_part.data() + k * npart * xb);
         if (rcs[k]) errs[k] = g_err;
       });
     }

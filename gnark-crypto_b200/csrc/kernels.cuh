@@ -186,6 +186,48 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
   }
 }
 
+// K1c (window-table mode, see k_table_level): all W windows feed ONE bucket set -- the entry of (scalar i,
+// window j) is the table point j*row_stride + i = 2^(c*j) * P_i, and hist / offsets are indexed by the bucket
+// alone.  The L2-residency argument of k_scatter_window is kept by passing over the digits once per BUCKET RANGE
+// [blo, bhi): a range owns a contiguous slice of `entries` (~4n bytes for uniform digits), every pass streams
+// all n*W digits (coalesced) and scatters only the ones of its range.  blockIdx.y = window.
+static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, uint32_t n, uint32_t row_stride,
+                                        uint32_t* __restrict__ hist, const uint32_t* __restrict__ offsets,
+                                        uint32_t* __restrict__ entries, uint32_t blo, uint32_t bhi) {
+  constexpr int U = 4;
+  const uint32_t tile = blockDim.x * U;
+  const uint32_t j = blockIdx.y;
+  const uint32_t* digits_w = digits + (size_t)j * n;
+  const uint32_t idx0 = j * row_stride;      // (W * row_stride) < 2^31 is checked by the host
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n; base += (uint64_t)gridDim.x * tile) {
+    uint32_t code[U], old[U], off[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+      code[u] = (i < n) ? __ldg(digits_w + i) : 0u;
+      if (code[u]) {
+        const uint32_t b = code_bucket(code[u]);
+        if (b < blo || b >= bhi) code[u] = 0u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t b = code_bucket(code[u]);
+        old[u] = atomicSub(&hist[b], 1u);
+        off[u] = offsets[b];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t i = (uint32_t)(base + (uint64_t)u * blockDim.x + threadIdx.x);
+        entries[off[u] + old[u] - 1u] = ((idx0 + i) << 1) | (code[u] & 1u);
+      }
+    }
+  }
+}
+
 // test hook: digits in the reference's encoding (multiexp.go:779-785), out[w*n + i]
 template <class G>
 __global__ void k_digits_dump(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
@@ -568,6 +610,53 @@ k_generate_multiples(const Affine<typename G::F>* __restrict__ base_p, uint64_t 
       F i2 = f_mul(f_sqr(pts[i].zz), f_sqr(i3));  // 1/ZZ_i
       a.x = f_mul(pts[i].x, i2);
       a.y = f_mul(pts[i].y, i3);
+    }
+    store_vec(out + first + i, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Window tables for resident bases: out[i] = 2^c * in[i] (affine).  Row j of a table holds 2^(c*j) * P_i, so
+//   sum_i s_i P_i = sum_j sum_i d_ij * (2^(c*j) P_i)
+// becomes ONE bucket problem over n*W table points with the digits of partitionScalars (multiexp.go:709-803)
+// -- no per-window bucket sets, no Horner (msmReduceChunk, multiexp.go:302-315, degenerates to one window),
+// which lets c grow to ~22 (W = 12 instead of 15 -> 20 % fewer bucket additions).  The reference has no
+// counterpart: its bases are re-read per call; this is the "static SRS" flow of kzg.Commit (kzg/kzg.go:159-176).
+// One thread takes TAB_M consecutive points: c Jacobian doublings each (dbl-2009-l), one shared inversion
+// (Montgomery's trick over the Z's), affine normal forms out.  Infinity stays (0, 0).
+// ------------------------------------------------------------------------------------------
+static constexpr int TAB_M = 8;
+template <class F>
+__device__ __noinline__ Jac<F> jac_double_cold(const Jac<F>& p) {
+  return jac_double(p);
+}
+template <class G>
+__global__ void __launch_bounds__(128)
+k_table_level(const Affine<typename G::F>* __restrict__ in, uint32_t n, int c, Affine<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * TAB_M;
+  if (first >= n) return;
+  const int cnt = (n - first < (uint64_t)TAB_M) ? (int)(n - first) : TAB_M;
+  Jac<F> pts[TAB_M];
+  F pref[TAB_M];
+  F prod = F::one();
+  for (int i = 0; i < cnt; i++) {
+    const Affine<F> a = load_vec_ro(in + first + i);
+    Jac<F> j = a.is_inf() ? Jac<F>{F::zero(), F::zero(), F::zero()} : Jac<F>{a.x, a.y, F::one()};
+    for (int l = 0; l < c; l++) j = jac_double_cold(j);
+    pts[i] = j;
+    pref[i] = prod;   // product of the non-zero Z's before i
+    if (!j.z.is_zero()) prod = f_mul(prod, j.z);
+  }
+  F inv = f_inv(prod);
+  for (int i = cnt - 1; i >= 0; i--) {
+    Affine<F> a = Affine<F>::inf();
+    if (!pts[i].z.is_zero()) {
+      const F zi = f_mul(inv, pref[i]);   // 1 / Z_i
+      inv = f_mul(inv, pts[i].z);
+      const F z2 = f_sqr(zi);
+      a.x = f_mul(pts[i].x, z2);
+      a.y = f_mul(f_mul(pts[i].y, z2), zi);
     }
     store_vec(out + first + i, a);
   }

@@ -176,6 +176,12 @@ class ResidentBases:
         _check(rc)
         return out
 
+    def Precompute(self, c: int = 0) -> int:
+        """gmsm_bases_precompute: replace the device copy of the bases by window tables (row j = 2^(c*j) * bases);
+        later MultiExp calls are bit-identical and ~20 % faster.  Returns the table window width."""
+        _check(_native.lib().gmsm_bases_precompute(self._h, int(c)))
+        return _native.lib().gmsm_bases_table_bits(self._h)
+
     def close(self):
         if self._h:
             _native.lib().gmsm_bases_free(self._h)
@@ -192,7 +198,7 @@ class Engine:
     """Device-level engine (gmsm_ctx_*): inputs already resident in HBM as torch uint8/int64 tensors.
     torch is used for device memory and streams only."""
 
-    def __init__(self, curve: str, max_n: int, c: int = 0, device: int = 0):
+    def __init__(self, curve: str, max_n: int, c: int = 0, device: int = 0, tables: bool = False):
         import torch
 
         self.torch = torch
@@ -200,8 +206,9 @@ class Engine:
         self.cid = CURVES[curve]
         self.w = _words(self.cid)
         self.device = device
+        self.tables = tables
         L = _native.lib()
-        self._h = L.gmsm_ctx_create(self.cid, max_n, c, device)
+        self._h = (L.gmsm_ctx_create_tables if tables else L.gmsm_ctx_create)(self.cid, max_n, c, device)
         if not self._h:
             raise MultiExpError(_native.last_error())
         self.c = L.gmsm_ctx_window_bits(self._h)
@@ -225,6 +232,25 @@ class Engine:
         if n is None:
             n = d_scalars.numel() // 4
         rc = _native.lib().gmsm_ctx_msm_device(self._h, d_points.data_ptr(), d_scalars.data_ptr(), n, self._out.data_ptr(), self._stream())
+        _check(rc)
+        return self._out
+
+    # ---- window-table mode (Engine(..., tables=True)) ----
+    def build_tables(self, d_points, n: int = None):
+        """device tensor of nwin rows of n affine points, row j = 2^(c*j) * points (gmsm_tables_build_device)"""
+        if n is None:
+            n = d_points.numel() // (2 * self.w)
+        tab = self.torch.empty(self.nwin * n * 2 * self.w, dtype=self.torch.int64, device=d_points.device)
+        with self.torch.cuda.device(self.device):
+            rc = _native.lib().gmsm_tables_build_device(self.cid, self.c, d_points.data_ptr(), n, tab.data_ptr(), n, self._stream())
+        _check(rc)
+        return tab
+
+    def msm_tables(self, d_table, row_stride: int, d_scalars, n: int = None, offset: int = 0):
+        if n is None:
+            n = d_scalars.numel() // 4
+        rc = _native.lib().gmsm_ctx_msm_tables_device(self._h, d_table.data_ptr(), row_stride, offset, d_scalars.data_ptr(), n,
+                                                      self._out.data_ptr(), self._stream())
         _check(rc)
         return self._out
 

@@ -97,6 +97,14 @@ gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size
 int gmsm_bases_multiexp(gmsm_bases_t* bases, size_t offset, const uint64_t* scalars, size_t n,
                         int nb_tasks, uint64_t* out_jac);
 void gmsm_bases_free(gmsm_bases_t* bases);
+/* Window tables for resident bases (no reference counterpart: the reference re-reads its bases on every call; this
+ * serves the static-SRS flow of kzg.Commit, kzg/kzg.go:159-176).  Replaces the device copy of the bases by a table of
+ * W rows, row j = 2^(c*j) * bases (W x the device memory, built once on the GPU).  Afterwards gmsm_bases_multiexp
+ * runs ONE bucket set over the n*W table points with the signed digits of partitionScalars (multiexp.go:709-803):
+ * no per-window bucket reduction, no Horner (msmReduceChunk), wider windows (c = 22, W = 12 at n = 2^24 instead of
+ * c = 17, W = 15).  Results are bit-identical.  c = 0: width from the cost model. */
+int gmsm_bases_precompute(gmsm_bases_t* bases, int c);
+int gmsm_bases_table_bits(const gmsm_bases_t* bases);   /* c of the tables, 0 if none */
 
 /* ---- 3. device-level engine (device pointers; what bench.py times with inputs resident in HBM and
  * what the multi-GPU path composes).  `stream` is a cudaStream_t (NULL = default stream). ---- */
@@ -122,6 +130,15 @@ int gmsm_ctx_window_sums_device(gmsm_ctx_t* ctx, const void* d_points, const voi
  * (msmReduceChunk, multiexp.go:302-315), normalise; d_out_jac as above */
 int gmsm_ctx_finalize_device(gmsm_ctx_t* ctx, const void* d_partials, int nranks, void* d_out_jac,
                              void* stream);
+/* window-table mode at device level (what gmsm_bases_precompute composes): the context shares one bucket set
+ * between all windows; d_table holds gmsm_ctx_num_windows(ctx) rows of row_stride affine points, row j =
+ * 2^(c*j) * row 0, built by gmsm_tables_build_device (current device; d_table may alias d_points for row 0).
+ * gmsm_ctx_msm_tables_device computes the MSM of scalars[0, n) with the bases row0[offset, offset + n). */
+gmsm_ctx_t* gmsm_ctx_create_tables(gmsm_curve_t curve, size_t max_n, int c, int device);
+int gmsm_tables_build_device(gmsm_curve_t curve, int c, const void* d_points, size_t n, void* d_table,
+                             size_t row_stride, void* stream);
+int gmsm_ctx_msm_tables_device(gmsm_ctx_t* ctx, const void* d_table, size_t row_stride, size_t offset,
+                               const void* d_scalars, size_t n, void* d_out_jac, void* stream);
 /* timings of the last msm call's stages in milliseconds (CUDA events on the call's stream), filled only
  * when enabled with gmsm_ctx_set_profiling(ctx, 1): [digits+hist, scan, scatter, accumulate,
  * carries, bucket-reduce, finalize, total] */

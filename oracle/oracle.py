@@ -702,6 +702,37 @@ def multi_exp(G: Group, points, scalars_mont, c=None):
     return G.jac_to_affine(inner_msm(G, c, points, scalars_mont))
 
 
+def multi_exp_tables(G: Group, points, scalars_mont, c: int):
+    """The window-table restatement the GPU engine uses for resident bases (gmsm_bases_precompute; no counterpart in
+    the reference, which re-reads its bases per call): table row j = 2^(c*j) * points, so that
+    sum_i s_i P_i = sum_j sum_i d_ij (2^(c*j) P_i) is ONE bucket problem over the digits of partitionScalars
+    (multiexp.go:709-803) with max(2^(c-1), 2^(lastC-1)) shared buckets -- no Horner (multiexp.go:302-315).
+    Its agreement with multi_exp() is what tests/test_oracle.py checks. -> affine."""
+    fr = G.fr
+    W = compute_nb_chunks(fr.bits, c)
+    digits = partition_scalars(fr, scalars_mont, c)
+    rows = [list(points)]
+    for j in range(1, W):
+        rows.append([G.aff_inf() if G.aff_is_inf(p) else G.scalar_mul(p, 1 << c) for p in rows[-1]])
+    nb = max(1 << (c - 1), 1 << (last_c(fr.bits, c) - 1))
+    buckets = [G.xyzz_inf() for _ in range(nb)]
+    for j in range(W):
+        for i, e in enumerate(digits[j]):
+            e = int(e)
+            if e == 0:
+                continue
+            if e & 1 == 0:
+                buckets[(e >> 1) - 1] = G.add_mixed(buckets[(e >> 1) - 1], rows[j][i])
+            else:
+                buckets[e >> 1] = G.add_mixed(buckets[e >> 1], rows[j][i], negate=True)
+    run, tot = G.xyzz_inf(), G.xyzz_inf()
+    for k in range(nb - 1, -1, -1):
+        if not G.K.is_zero(buckets[k][2]):
+            run = G.xyzz_add(run, buckets[k])
+        tot = G.xyzz_add(tot, run)
+    return G.jac_to_affine(G.xyzz_to_jac(tot))
+
+
 def msm_naive(G: Group, points, ks):
     """sum k_i * P_i by independent double-and-add (independent of the bucket method)."""
     acc = G.aff_inf()

@@ -177,6 +177,23 @@ def test_msm_all_c_agree(g):
         assert O.multi_exp(G, pts, sm, c=c) == expect, c
 
 
+@pytest.mark.parametrize("g,cs", [("bn254_g1", [2, 5, 8, 13]), ("bls12381_g1", [5, 11]), ("bn254_g2", [7])])
+def test_msm_window_tables_agree(g, cs):
+    """the window-table formulation (row j = 2^(c*j) * bases, one shared bucket set, no Horner) gives the
+    reference's MultiExp result for every c, incl. c = 2 / 5 where lastC = c + 1 (the last window's bucket
+    range exceeds 2^(c-1))"""
+    G = O.GROUPS[g]
+    n = 40 if g == "bn254_g1" else 14
+    pts, ks = _inputs(G, n, 9, n_inf=3)
+    ks[3] = 0
+    ks[5] = G.fr.q - 1
+    sm = [G.fr.to_mont(k) for k in ks]
+    expect = O.msm_naive(G, pts, ks)
+    for c in cs:
+        assert O.multi_exp_tables(G, pts, sm, c) == expect, c
+        assert O.multi_exp(G, pts, sm, c=c) == expect, c
+
+
 def test_msm_closed_form():
     # multiexp_test.go:186-216 : 30 points [i]G with scalars i*mixer -> [sum i^2 * mixer]G = [9455*mixer]G
     G = O.GROUPS["bn254_g1"]
