@@ -76,6 +76,35 @@ struct Group {
     return a;
   }
 
+  // Resident bases (gmsm_bases_*): the static-SRS flow of kzg.Commit (kzg/kzg.go:159-176 passes pk.G1[:len(p)]):
+  // bases uploaded once, scalars per call.  Precompute() replaces them by window tables (gmsm_bases_precompute).
+  class ResidentBases {
+   public:
+    explicit ResidentBases(const std::vector<Affine>& points, int device = 0)
+        : n_(points.size()), h_(gmsm_bases_upload(CURVE, points.empty() ? nullptr : points[0].X.data(), points.size(), device)) {
+      if (!h_) throw Error(gmsm_last_error());
+    }
+    ResidentBases(const ResidentBases&) = delete;
+    ResidentBases& operator=(const ResidentBases&) = delete;
+    ~ResidentBases() { gmsm_bases_free(h_); }
+    // MultiExp over bases[offset, offset + len(scalars))
+    Jac MultiExp(const std::vector<Scalar>& scalars, MultiExpConfig config = {}, size_t offset = 0) const {
+      if (offset > n_ || scalars.size() > n_ - offset) throw Error("len(points) != len(scalars)");
+      Jac j;
+      int rc = gmsm_bases_multiexp(h_, offset, scalars.empty() ? nullptr : scalars[0].data(), scalars.size(), config.NbTasks, j.X.data());
+      if (rc != GMSM_OK) throw Error(gmsm_last_error());
+      return j;
+    }
+    int Precompute(int c = 0) {   // returns the table window width
+      if (gmsm_bases_precompute(h_, c) != GMSM_OK) throw Error(gmsm_last_error());
+      return gmsm_bases_table_bits(h_);
+    }
+
+   private:
+    size_t n_;
+    gmsm_bases_t* h_;
+  };
+
   // BatchScalarMultiplicationG1 / G2 (g1.go:1039-1118)
   static std::vector<Affine> BatchScalarMultiplication(const Affine& base, const std::vector<Scalar>& scalars) {
     std::vector<Affine> out(scalars.size());
@@ -102,5 +131,13 @@ using G1Jac = G1::Jac;
 using G2Affine = G2::Affine;
 using G2Jac = G2::Jac;
 }  // namespace bls12381
+namespace bls12377 {   // ecc/bls12-377
+using G1 = Group<GMSM_BLS12377_G1, 6, 1>;
+using G2 = Group<GMSM_BLS12377_G2, 6, 2>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+using G2Affine = G2::Affine;
+using G2Jac = G2::Jac;
+}  // namespace bls12377
 
 }  // namespace gmsm_host

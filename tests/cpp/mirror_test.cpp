@@ -41,6 +41,17 @@ int main(int argc, char** argv) {
     CHECK(j.IsInfinity());
     auto bs = bn254::G1::BatchScalarMultiplication(G, {zero, one});
     CHECK(bs[0].IsInfinity() && bs[1] == G);
+    // resident bases, before and after the window tables: G + G = [2]G, sub-range, reference error string
+    bn254::G1::ResidentBases rb({G, G, G2x});
+    for (int pass = 0; pass < 2; pass++) {
+      auto r2 = rb.MultiExp({one, one});
+      CHECK(r2.X == G2x.X && r2.Y == G2x.Y && !r2.IsInfinity());
+      auto r1 = rb.MultiExp({one}, {}, 2);
+      CHECK(r1.X == G2x.X && r1.Y == G2x.Y);
+      try { rb.MultiExp({one, one}, {}, 2); CHECK(false); }
+      catch (const Error& e) { CHECK(std::string(e.what()) == "len(points) != len(scalars)"); }
+      if (pass == 0) CHECK(rb.Precompute(5) == 5);
+    }
   }
   std::printf(fails ? "MIRROR_FAILED\n" : "MIRROR_OK\n");
   return fails ? 1 : 0;

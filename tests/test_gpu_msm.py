@@ -284,6 +284,19 @@ def test_kzg_commit_over_generated_srs_and_dump_roundtrip(tmp_path):
     f_alpha = sum(c * pow(alpha, i, r) for i, c in enumerate(coeffs)) % r
     digest = kzg.Commit(G.encode_scalars(coeffs), pk)
     assert np.array_equal(digest, cref.scalar_mul(g, gen, f_alpha))
+    # kzg.Open (kzg.go:180-204): ClaimedValue = f(a), H = [h(alpha)]G with h = (f - f(a)) / (X - a)
+    a = 0xDEADBEEF12345
+    proof = kzg.Open(G.encode_scalars(coeffs), G.encode_scalars([a])[0], pk)
+    f_a = sum(c * pow(a, i, r) for i, c in enumerate(coeffs)) % r
+    assert np.array_equal(proof.ClaimedValue, G.encode_scalars([f_a])[0])
+    h_alpha = (f_alpha - f_a) * pow(alpha - a, -1, r) % r
+    assert np.array_equal(proof.H, cref.scalar_mul(g, gen, h_alpha))
+    with pytest.raises(kzg.ErrInvalidPolynomialSize):
+        kzg.Open(G.encode_scalars([5]), G.encode_scalars([a])[0], pk)      # constant polynomial: empty quotient
+    # the same key with window tables (static SRS): identical digest
+    pk2 = kzg.ProvingKey("bn254", srs[:2048], window_tables=True)
+    assert np.array_equal(kzg.Commit(G.encode_scalars(coeffs), pk2), digest)
+    pk2.close()
     with pytest.raises(kzg.ErrInvalidPolynomialSize):
         kzg.Commit(G.encode_scalars([1] * 2049), pk)
     with pytest.raises(kzg.ErrInvalidPolynomialSize):
