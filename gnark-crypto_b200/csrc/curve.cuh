@@ -168,6 +168,39 @@ GMSM_HD Jac<F> jac_double(const Jac<F>& p) {
   return r;
 }
 
+// One batch of a window-table level (k_table_level, kernels.cuh): out_i = 2^c * in_i for cnt <= TAB_M affine points,
+// c Jacobian doublings each and ONE shared inversion (Montgomery's trick over the non-zero Z's).  Infinity -- on
+// input, or reached by the doublings (a point of 2-power order) -- stays (0, 0).  ld(i) / st(i, a) / dbl(j) are the
+// caller's load, store and doubling (the kernel passes 256-bit loads and an out-of-line doubling; the CPU formula
+// check of tests/test_hostcheck.py passes plain ones).
+static constexpr int TAB_M = 8;
+template <class F, class Ld, class St, class Dbl>
+GMSM_HD void table_level_batch(int cnt, int c, Ld ld, St st, Dbl dbl) {
+  Jac<F> pts[TAB_M];
+  F pref[TAB_M];
+  F prod = F::one();
+  for (int i = 0; i < cnt; i++) {
+    const Affine<F> a = ld(i);
+    Jac<F> j = a.is_inf() ? Jac<F>{F::zero(), F::zero(), F::zero()} : Jac<F>{a.x, a.y, F::one()};
+    for (int l = 0; l < c; l++) j = dbl(j);
+    pts[i] = j;
+    pref[i] = prod;   // product of the non-zero Z's before i
+    if (!j.z.is_zero()) prod = f_mul(prod, j.z);
+  }
+  F inv = f_inv(prod);
+  for (int i = cnt - 1; i >= 0; i--) {
+    Affine<F> a = Affine<F>::inf();
+    if (!pts[i].z.is_zero()) {
+      const F zi = f_mul(inv, pref[i]);   // 1 / Z_i
+      inv = f_mul(inv, pts[i].z);
+      const F z2 = f_sqr(zi);
+      a.x = f_mul(pts[i].x, z2);
+      a.y = f_mul(f_mul(pts[i].y, z2), zi);
+    }
+    st(i, a);
+  }
+}
+
 // Jacobian (X, Y, Z) -> extended Jacobian (X, Y, Z^2, Z^3): same X, Y
 template <class F>
 GMSM_HD XYZZ<F> jac_to_xyzz(const Jac<F>& p) {

@@ -38,6 +38,18 @@ using HcG = bls12377_g2;
 extern "C" int HC_CAT(hostcheck_op_, HC_GROUP)(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   return run<HcG>(op, a, b, o, n);
 }
+// one window-table level on the CPU, batched exactly like k_table_level: out[i] = 2^c * in[i] (affine, u32 words)
+extern "C" int HC_CAT(hostcheck_table_level_, HC_GROUP)(int c, const uint32_t* in, size_t n, uint32_t* out) {
+  using F = typename HcG::F;
+  constexpr int AW = 2 * F::N;
+  for (size_t first = 0; first < n; first += TAB_M) {
+    const int cnt = (n - first < (size_t)TAB_M) ? (int)(n - first) : TAB_M;
+    table_level_batch<F>(
+        cnt, c, [&](int i) { return rd<Affine<F>>(in + (first + i) * AW); },
+        [&](int i, const Affine<F>& a) { wr(out + (first + i) * AW, a); }, [](const Jac<F>& j) { return jac_double(j); });
+  }
+  return 0;
+}
 #else
 extern "C" {
 int hostcheck_op_0(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
@@ -46,6 +58,25 @@ int hostcheck_op_2(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
 int hostcheck_op_3(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
 int hostcheck_op_4(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
 int hostcheck_op_5(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+}
+extern "C" {
+int hostcheck_table_level_0(int, const uint32_t*, size_t, uint32_t*);
+int hostcheck_table_level_1(int, const uint32_t*, size_t, uint32_t*);
+int hostcheck_table_level_2(int, const uint32_t*, size_t, uint32_t*);
+int hostcheck_table_level_3(int, const uint32_t*, size_t, uint32_t*);
+int hostcheck_table_level_4(int, const uint32_t*, size_t, uint32_t*);
+int hostcheck_table_level_5(int, const uint32_t*, size_t, uint32_t*);
+}
+extern "C" int hostcheck_table_level(int curve, int c, const uint32_t* in, size_t n, uint32_t* out) {
+  switch (curve) {
+    case 0: return hostcheck_table_level_0(c, in, n, out);
+    case 1: return hostcheck_table_level_1(c, in, n, out);
+    case 2: return hostcheck_table_level_2(c, in, n, out);
+    case 3: return hostcheck_table_level_3(c, in, n, out);
+    case 4: return hostcheck_table_level_4(c, in, n, out);
+    case 5: return hostcheck_table_level_5(c, in, n, out);
+  }
+  return 1;
 }
 extern "C" int hostcheck_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   switch (curve) {

@@ -622,10 +622,9 @@ k_generate_multiples(const Affine<typename G::F>* __restrict__ base_p, uint64_t 
 // -- no per-window bucket sets, no Horner (msmReduceChunk, multiexp.go:302-315, degenerates to one window),
 // which lets c grow to ~22 (W = 12 instead of 15 -> 20 % fewer bucket additions).  The reference has no
 // counterpart: its bases are re-read per call; this is the "static SRS" flow of kzg.Commit (kzg/kzg.go:159-176).
-// One thread takes TAB_M consecutive points: c Jacobian doublings each (dbl-2009-l), one shared inversion
-// (Montgomery's trick over the Z's), affine normal forms out.  Infinity stays (0, 0).
+// One thread takes TAB_M consecutive points (table_level_batch, curve.cuh): c Jacobian doublings each (dbl-2009-l),
+// one shared inversion (Montgomery's trick over the Z's), affine normal forms out.  Infinity stays (0, 0).
 // ------------------------------------------------------------------------------------------
-static constexpr int TAB_M = 8;
 template <class F>
 __device__ __noinline__ Jac<F> jac_double_cold(const Jac<F>& p) {
   return jac_double(p);
@@ -637,29 +636,9 @@ k_table_level(const Affine<typename G::F>* __restrict__ in, uint32_t n, int c, A
   const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * TAB_M;
   if (first >= n) return;
   const int cnt = (n - first < (uint64_t)TAB_M) ? (int)(n - first) : TAB_M;
-  Jac<F> pts[TAB_M];
-  F pref[TAB_M];
-  F prod = F::one();
-  for (int i = 0; i < cnt; i++) {
-    const Affine<F> a = load_vec_ro(in + first + i);
-    Jac<F> j = a.is_inf() ? Jac<F>{F::zero(), F::zero(), F::zero()} : Jac<F>{a.x, a.y, F::one()};
-    for (int l = 0; l < c; l++) j = jac_double_cold(j);
-    pts[i] = j;
-    pref[i] = prod;   // product of the non-zero Z's before i
-    if (!j.z.is_zero()) prod = f_mul(prod, j.z);
-  }
-  F inv = f_inv(prod);
-  for (int i = cnt - 1; i >= 0; i--) {
-    Affine<F> a = Affine<F>::inf();
-    if (!pts[i].z.is_zero()) {
-      const F zi = f_mul(inv, pref[i]);   // 1 / Z_i
-      inv = f_mul(inv, pts[i].z);
-      const F z2 = f_sqr(zi);
-      a.x = f_mul(pts[i].x, z2);
-      a.y = f_mul(f_mul(pts[i].y, z2), zi);
-    }
-    store_vec(out + first + i, a);
-  }
+  table_level_batch<F>(
+      cnt, c, [&](int i) { return load_vec_ro(in + first + i); }, [&](int i, const Affine<F>& a) { store_vec(out + first + i, a); },
+      [](const Jac<F>& j) { return jac_double_cold(j); });
 }
 
 // ------------------------------------------------------------------------------------------

@@ -73,6 +73,31 @@ def test_point_ops_host(hc, g):
     opcases.check_point_ops(O.GROUPS[g], _runner(hc, g))
 
 
+@pytest.mark.parametrize("g,c", [("bn254_g1", 5), ("bn254_g1", 22), ("bn254_g2", 7), ("bls12381_g1", 11), ("bls12381_g2", 3),
+                                 ("bls12377_g1", 9), ("bls12377_g2", 4)])
+def test_table_level_host(hc, g, c):
+    """one level of the window tables (k_table_level's batch function, built for the CPU): out_i = 2^c * in_i in affine
+    normal form, infinity preserved, ragged batch (19 = 2 full batches of 8 + 3)"""
+    G = O.GROUPS[g]
+    pts = O.consecutive_multiples(G, 19, start_k=3)
+    pts[4] = G.aff_inf()
+    pts[16] = G.aff_inf()
+    pts[9] = pts[8]
+    arr = np.ascontiguousarray(G.encode_affine(pts)).view(np.uint32).reshape(19, -1)
+    out = np.zeros_like(arr)
+    rc = hc.hostcheck_table_level(list(O.GROUPS).index(g), c, arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(19),
+                                  out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    want = [G.aff_inf() if G.aff_is_inf(p) else G.scalar_mul(p, 1 << c) for p in pts]
+    assert np.array_equal(out.view(np.uint64).reshape(19, -1), G.encode_affine(want))
+    # all-infinity batch: the shared inversion runs on the empty product
+    z = np.zeros_like(arr[:5])
+    o2 = np.ones_like(z)
+    assert hc.hostcheck_table_level(list(O.GROUPS).index(g), c, z.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(5),
+                                    o2.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert not o2.any()
+
+
 def test_window_plan(hc):
     buf = (ctypes.c_int * 6)()
     for bits in (253, 254, 255):

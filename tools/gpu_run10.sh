@@ -1,7 +1,7 @@
 #!/bin/bash
 # window-table mode: parity tests, default bench line (incl. resident_tables), table-width sweep
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_tables.py -x -q -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/r10_pytest_tables.log
+timeout 900 python -m pytest tests/test_gpu_tables.py tests/test_cpp_mirror.py "tests/test_gpu_msm.py::test_kzg_commit_over_generated_srs_and_dump_roundtrip" -x -q -m gpu -p no:cacheprovider 2>&1 | tail -15 | tee gpurun_out/r10_pytest_tables.log
 timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 2>gpurun_out/r10_b.err | tee gpurun_out/r10_bench_default.json | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['stages_ms']); print(d.get('resident_tables')); print(d['e2e']); print(d.get('e2e_resident_bases')); print(d.get('e2e_resident_tables')); print(d['clocks'])"
 tail -3 gpurun_out/r10_b.err
