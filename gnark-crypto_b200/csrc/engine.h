@@ -42,6 +42,7 @@ struct gmsm_ctx {
   // finalize see a single window.  tab_stride = points per table row (set by the caller before each accumulate).
   bool shared = false;
   uint32_t tab_stride = 0;
+  int table_passes = 0;   // bucket-range passes of the shared scatter (0 = one per window; GMSM_TABLE_PASSES)
   int red_windows() const { return shared ? 1 : plan.nwin; }   // partials per call
   // chunking
   uint32_t K2 = 16;

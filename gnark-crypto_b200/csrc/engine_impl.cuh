@@ -62,9 +62,10 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   // blocks leave no room for co-resident scatter blocks -> G1 groups only)
   // Window-table mode: one pass per bucket range instead of one per window (k_scatter_shared); the ranges play
   // the role of the windows for the overlap with the accumulate.
-  const int NPASS = p.nwin;
+  int NPASS = p.nwin;
+  if (c->shared && c->table_passes > 0) NPASS = c->table_passes;
   const uint32_t range_sz = c->shared ? (p.nb_total + (uint32_t)NPASS - 1) / (uint32_t)NPASS : p.nb;
-  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->split_w, p.nwin) : p.nwin;
+  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->split_w, NPASS) : NPASS;
   if (c->shared) {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 2u);
     auto scatter = [&](int r, cudaStream_t s) {
@@ -90,7 +91,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
                                               c->offsets + (size_t)j * p.nb, c->entries);
       launches++;
     };
-    if (SPLIT_W < p.nwin) {
+    if (SPLIT_W < NPASS) {
       CK(cudaEventRecord(c->ev_split[0], st));           // scan done: offsets, digits, hist are ready
       CK(cudaStreamWaitEvent(c->aux, c->ev_split[0], 0));
       for (int j = SPLIT_W; j < p.nwin; j++) scatter(j, c->aux);
@@ -171,7 +172,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
     CK(cudaMemsetAsync(buckets, 0, (size_t)p.nb_total * sizeof(X), st));
     {
       X* carr = reinterpret_cast<X*>(c->carries[0]);
-      if (SPLIT_W < p.nwin) {
+      if (SPLIT_W < NPASS) {
         const uint32_t split_bucket = (uint32_t)std::min<uint64_t>((uint64_t)SPLIT_W * range_sz, p.nb_total);
         k_accumulate<G><<<nblk(nchunks, 128), 128, 0, st>>>(points, c->entries, c->offsets, p.nb_total, K, (uint32_t)nchunks,
                                                             buckets, carr, c->carry_ids[0], 1, split_bucket);

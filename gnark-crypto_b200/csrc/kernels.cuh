@@ -341,6 +341,9 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 #ifndef GMSM_ACC_MINBLOCKS_BIG
 #define GMSM_ACC_MINBLOCKS_BIG 1
 #endif
+#ifndef GMSM_ACC_PREFETCH_BEND
+#define GMSM_ACC_PREFETCH_BEND 1
+#endif
 template <class G>
 __global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : GMSM_ACC_MINBLOCKS_BIG)
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
@@ -369,6 +372,11 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
 
   uint32_t b = upper_bound_u32(offsets, nb_total + 1, start) - 1u;
   uint32_t bend = offsets[b + 1];
+  // end of the NEXT bucket, fetched one bucket ahead so that a boundary costs no dependent load (the warp is
+  // divergent there: every lane waits for it).  offsets[] is padded past nb_total; the pad is never consumed.
+#if GMSM_ACC_PREFETCH_BEND
+  uint32_t bend2 = offsets[b + 2];
+#endif
   bool owner = (offsets[b] == start);
   uint32_t my_carry = ID_NONE;
   XYZZ<F> acc = XYZZ<F>::inf();
@@ -393,8 +401,17 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
         my_carry = b;
       }
       b++;
+#if GMSM_ACC_PREFETCH_BEND
+      bend = bend2;
+      if (bend == pos) {   // skip empty buckets
+        b = upper_bound_u32(offsets, nb_total + 1, pos) - 1u;
+        bend = offsets[b + 1];
+      }
+      bend2 = offsets[b + 2];
+#else
       if (offsets[b + 1] == pos) b = upper_bound_u32(offsets, nb_total + 1, pos) - 1u;  // skip empty buckets
       bend = offsets[b + 1];
+#endif
       owner = true;
       acc = XYZZ<F>::inf();
     }
