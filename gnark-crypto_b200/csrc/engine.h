@@ -42,7 +42,7 @@ struct gmsm_ctx {
   // finalize see a single window.  tab_stride = points per table row (set by the caller before each accumulate).
   bool shared = false;
   uint32_t tab_stride = 0;
-  int table_passes = 0;   // bucket-range passes of the shared scatter (0 = one per window; GMSM_TABLE_PASSES)
+  int table_passes = 0;   // bucket-range passes of the shared scatter (0 = from the entry count; GMSM_TABLE_PASSES)
   int red_windows() const { return shared ? 1 : plan.nwin; }   // partials per call
   // chunking
   uint32_t K2 = 16;
@@ -78,6 +78,7 @@ struct gmsm_ctx {
   bool profiling = false;
   cudaEvent_t ev[9] = {};
   int split_w = 2;                     // windows scattered before the accumulate starts (GMSM_SPLIT_W)
+  int split_tab = 1;                   // the same for the bucket-range passes of the window-table mode
   cudaStream_t aux = nullptr;          // auxiliary stream: scatter of the later windows under the accumulate
   cudaEvent_t ev_split[2] = {};
   float stage_ms[8] = {};

@@ -62,10 +62,16 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   // blocks leave no room for co-resident scatter blocks -> G1 groups only)
   // Window-table mode: one pass per bucket range instead of one per window (k_scatter_shared); the ranges play
   // the role of the windows for the overlap with the accumulate.
+  // (measured at bn254 G1 n = 2^24, c = 22, profiles/r01_table_passes_bn254g1_v12.txt: every pass streams all n*W
+  // digits, so few passes win even though a pass's slice -- ~200 MB -- exceeds L2: 4 passes with one of them ahead
+  // of the accumulate 41.4 ms, 12 passes 44.4 ms, 1 pass 44.6 ms)
   int NPASS = p.nwin;
-  if (c->shared && c->table_passes > 0) NPASS = c->table_passes;
+  if (c->shared) {
+    const double slice = (double)n * p.nwin * 4.0 / 200e6;
+    NPASS = c->table_passes > 0 ? c->table_passes : (int)std::min(16.0, std::max(4.0, slice + 0.5));
+  }
   const uint32_t range_sz = c->shared ? (p.nb_total + (uint32_t)NPASS - 1) / (uint32_t)NPASS : p.nb;
-  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->split_w, NPASS) : NPASS;
+  const int SPLIT_W = (!c->affine && sizeof(F) <= 48 && p.nwin >= 6 && n >= (1u << 16)) ? std::min(c->shared ? c->split_tab : c->split_w, NPASS) : NPASS;
   if (c->shared) {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 2u);
     auto scatter = [&](int r, cudaStream_t s) {

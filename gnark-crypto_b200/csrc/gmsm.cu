@@ -223,7 +223,7 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
   if (shared) ctx->affine = false;   // the window-table mode has one accumulation path
   if (const char* e = getenv("GMSM_TABLE_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 256) ctx->table_passes = v; }
-  if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = v; }
+  if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = ctx->split_tab = v; }
   ctx->plan = make_plan(ci.fr_bits, c);
   if (shared) ctx->plan.nb_total = std::max(ctx->plan.nb, ctx->plan.nb_last);   // one bucket set for all windows
   if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
