@@ -46,6 +46,7 @@ struct gmsm_ctx {
   int red_windows() const { return shared ? 1 : plan.nwin; }   // partials per call
   // chunking
   uint32_t K2 = 16;
+  uint32_t K2_first = 16;   // items per thread of the first carry level (GMSM_K2_FIRST)
   uint32_t seg_L = 32, seg_S = 0;
   // device workspace
   uint32_t* hist = nullptr;      // nb_total + 1 (+pad)

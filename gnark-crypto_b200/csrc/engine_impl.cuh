@@ -199,9 +199,12 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
       size_t n_in = nchunks;
       int cur = 0;
       while (n_in > 1) {
-        size_t n_out = (n_in + c->K2 - 1) / c->K2;
+        // the first level carries nearly all the additions (one carry per chunk): a short run length there
+        // means more threads for the same work; the later levels see mostly empty slots
+        const uint32_t k2 = (cur == 0 && n_in == nchunks) ? c->K2_first : c->K2;
+        size_t n_out = (n_in + k2 - 1) / k2;
         k_carry_level<G><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
-                                                          (uint32_t)n_in, c->K2, buckets,
+                                                          (uint32_t)n_in, k2, buckets,
                                                           reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
         launches++;
         LAUNCH_CHECK();

@@ -139,7 +139,9 @@ static int ctx_alloc(gmsm_ctx* c) {
   c->max_chunks = mc;
   CK(dmalloc(&c->carries[0], mc * xyzz, &acc));
   CK(dmalloc(&c->carry_ids[0], (mc + 8) * 4, &acc));
-  size_t mc2 = (mc + c->K2 - 1) / c->K2;
+  if (const char* e = getenv("GMSM_K2_FIRST")) { int v = atoi(e); if (v >= 2 && v <= 64) c->K2_first = (uint32_t)v; }
+  const uint32_t k2min = std::min(c->K2, c->K2_first);
+  size_t mc2 = (mc + k2min - 1) / k2min;
   CK(dmalloc(&c->carries[1], mc2 * xyzz, &acc));
   CK(dmalloc(&c->carry_ids[1], (mc2 + 8) * 4, &acc));
   uint32_t nbmax = std::max(p.nb, p.nb_last);
