@@ -46,7 +46,8 @@ struct gmsm_ctx {
   int red_windows() const { return shared ? 1 : plan.nwin; }   // partials per call
   // chunking
   uint32_t K2 = 16;
-  uint32_t K2_first = 16;   // items per thread of the first carry level (GMSM_K2_FIRST)
+  uint32_t K2_first = 4;    // items per thread of the first carry level (GMSM_K2_FIRST): 4x the threads for the level that
+                            // holds nearly all the carry additions (measured 0.87 -> 0.73 ms at bn254 G1 2^24)
   uint32_t seg_L = 32, seg_S = 0;
   // device workspace
   uint32_t* hist = nullptr;      // nb_total + 1 (+pad)

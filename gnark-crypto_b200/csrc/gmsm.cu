@@ -415,10 +415,25 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   int nch = (n >= (1u << 21)) ? 5 : ((n >= (1u << 18)) ? 2 : 1);
   if (const char* e = getenv("GMSM_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) nch = v; }
   if ((size_t)nch > n) nch = 1;
+  // GMSM_SCHEDULE="1,2,3,5,8": explicit batch weights (experiments; overrides the counts above for n >= 2^18)
+  int wts[16], wsum = 0, nw = 0;
+  if (const char* e = getenv("GMSM_SCHEDULE")) {
+    if (n >= (1u << 18)) {
+      for (const char* q = e; *q && nw < 16;) {
+        char* end = nullptr;
+        long v = strtol(q, &end, 10);
+        if (end == q || v < 1 || v > 1000) break;
+        wts[nw++] = (int)v; wsum += (int)v;
+        q = (*end == ',') ? end + 1 : end;
+      }
+      if (nw >= 1) nch = nw;
+    }
+  }
   size_t bstart[17];
   bstart[0] = 0;
   for (int k = 1; k <= nch; k++) {
-    if (nch == 5) { int acc16 = 0; for (int u = 0; u < k; u++) acc16 += FR5[u]; bstart[k] = (k == nch) ? n : (n / 16) * acc16; }
+    if (nw >= 1) { long acc = 0; for (int u = 0; u < k; u++) acc += wts[u]; bstart[k] = (k == nch) ? n : (size_t)((double)n * acc / wsum); }
+    else if (nch == 5) { int acc16 = 0; for (int u = 0; u < k; u++) acc16 += FR5[u]; bstart[k] = (k == nch) ? n : (n / 16) * acc16; }
     else bstart[k] = (k == nch) ? n : (n / nch) * k;
   }
   size_t nc = 0;
@@ -617,23 +632,42 @@ extern "C" int gmsm_bases_precompute(gmsm_bases_t* b, int c) {
   const WindowPlan p = make_plan(ci.fr_bits, c);
   if ((double)max_sh * p.nwin >= 2147483000.0)
     return set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 31-bit table index; shard the bases", max_sh, p.nwin);
-  for (BaseShard& sh : b->shards) {
+  // build every shard's table first and switch all shards over only when all of them succeeded, so that a
+  // failure (typically GMSM_ENOMEM on one device) leaves the handle exactly as it was
+  std::vector<void*> tabs(b->shards.size(), nullptr);
+  int rc = GMSM_OK;
+  for (size_t k = 0; k < b->shards.size() && rc == GMSM_OK; k++) {
+    BaseShard& sh = b->shards[k];
     const size_t m = sh.hi - sh.lo;
-    CK(cudaSetDevice(sh.device));
-    void* tab = nullptr;
     const size_t bytes = m * (size_t)p.nwin * ab;
-    cudaError_t e = cudaMalloc(&tab, bytes ? bytes : 16);
-    if (e != cudaSuccess) return set_err(GMSM_ENOMEM, "window tables: %zu bytes on device %d: %s", bytes, sh.device, cudaGetErrorString(e));
-    int rc = gmsm_tables_build_device((gmsm_curve_t)b->curve, c, sh.d_points, m, tab, m, sh.pipe.comp_st);
+    cudaError_t e = cudaSetDevice(sh.device);
+    if (e == cudaSuccess) e = cudaMalloc(&tabs[k], bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+      cudaGetLastError();   // clear the (non-sticky) allocation error
+      rc = set_err(e == cudaErrorMemoryAllocation ? GMSM_ENOMEM : GMSM_ECUDA, "window tables: %zu bytes on device %d: %s", bytes,
+                   sh.device, cudaGetErrorString(e));
+      break;
+    }
+    rc = gmsm_tables_build_device((gmsm_curve_t)b->curve, c, sh.d_points, m, tabs[k], m, sh.pipe.comp_st);
     if (rc == GMSM_OK) {
       e = cudaStreamSynchronize(sh.pipe.comp_st);
       if (e != cudaSuccess) rc = set_err(GMSM_ECUDA, "window tables: %s", cudaGetErrorString(e));
     }
-    if (rc != GMSM_OK) { cudaFree(tab); return rc; }
+  }
+  if (rc != GMSM_OK) {
+    const std::string keep = g_err;
+    for (size_t k = 0; k < tabs.size(); k++)
+      if (tabs[k]) { cudaSetDevice(b->shards[k].device); cudaFree(tabs[k]); }
+    g_err = keep;
+    return rc;
+  }
+  for (size_t k = 0; k < b->shards.size(); k++) {
+    BaseShard& sh = b->shards[k];
+    cudaSetDevice(sh.device);
     cudaFree(sh.d_points);
-    sh.d_points = tab;
+    sh.d_points = tabs[k];
     sh.pipe.tables = true;
-    sh.pipe.tab_stride = m;
+    sh.pipe.tab_stride = sh.hi - sh.lo;
     sh.pipe.tab_c = c;
   }
   return GMSM_OK;
