@@ -412,12 +412,20 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   // batch sizes grow geometrically (1/16, 1/8, 3/16, 1/4, 3/8 of n): the first copy is short, and since the
   // GPU consumes a batch more slowly than PCIe delivers the next, every later copy hides under compute
   static const int FR5[5] = {1, 2, 3, 4, 6};   // sixteenths
+  const uint64_t* hp_in = h_points;
   int nch = (n >= (1u << 21)) ? 5 : ((n >= (1u << 18)) ? 2 : 1);
   if (const char* e = getenv("GMSM_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) nch = v; }
   if ((size_t)nch > n) nch = 1;
   // GMSM_SCHEDULE="1,2,3,5,8": explicit batch weights (experiments; overrides the counts above for n >= 2^18)
   int wts[16], wsum = 0, nw = 0;
+  if (!hp_in && n >= (1u << 21) && !getenv("GMSM_CHUNKS")) {
+    // resident bases: only the scalars (32 B each) cross PCIe, a third of the one-shot volume, so three batches are
+    // enough to hide the copies and every batch less saves its bucket merge + carry join (~1.1 ms each; measured
+    // profiles/r01_e2e_schedule_sweep_v15.txt: 4 batches 51.3 ms, 5 batches 52.2 ms at bn254 G1 2^24)
+    wts[0] = 1; wts[1] = 3; wts[2] = 9; nw = 3; wsum = 13; nch = 3;
+  }
   if (const char* e = getenv("GMSM_SCHEDULE")) {
+    nw = 0; wsum = 0;
     if (n >= (1u << 18)) {
       for (const char* q = e; *q && nw < 16;) {
         char* end = nullptr;
