@@ -1,4 +1,7 @@
 """helpers shared by the -m gpu tests"""
+import json
+import os
+
 import numpy as np
 
 from oracle import cref
@@ -31,3 +34,17 @@ def jac_to_affine_bytes(g, jac):
     """FromJacobian (g1.go:150-166) of the engine's output, via the oracle -> u64 affine limbs"""
     G = O.GROUPS[g]
     return G.encode_affine([G.jac_to_affine(G.decode_jac(jac))])[0]
+
+
+_GOLD = None
+
+
+def load_golden_msm(g):
+    """tests/golden/msm_vectors.json (made by tests/golden/make_msm_golden.py): points, scalars, expected affine result
+    as uint64 arrays in Go memory layout"""
+    global _GOLD
+    if _GOLD is None:
+        _GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msm_vectors.json")))["groups"]
+    v = _GOLD[g]
+    conv = lambda rows: np.array([[int(x, 16) for x in r] for r in rows], dtype=np.uint64)
+    return conv(v["points"]), conv(v["scalars"]), conv([v["result_affine"]])[0]

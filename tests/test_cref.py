@@ -163,3 +163,20 @@ def test_msm_batch_affine_processor(g, n):
         py = O.multi_exp(G, G.decode_affine(pts[:400]), [O.Field.from_limbs(r) for r in s[:400]], c=8)
         a, _, _, _ = cref.msm(g, pts[:400], s[:400], c=10, nthreads=2)
         assert np.array_equal(a, G.encode_affine([py])[0])
+
+
+@pytest.mark.parametrize("g", list(O.GROUPS))
+def test_golden_msm_vectors(g):
+    """the committed MultiExp known answers (tests/golden/msm_vectors.json) against the C port at the reference's own
+    window choice and at forced widths (batch-affine and extended-Jacobian processors), and against the Python oracle
+    at a width different from the one that generated them"""
+    from tests.gpu_common import load_golden_msm
+
+    pts, s, want = load_golden_msm(g)
+    G = O.GROUPS[g]
+    assert pts.shape == (96, G.aff_words) and s.shape == (96, 4)
+    for c in (0, 4, 9, 12, 16):
+        got, _, _, _ = cref.msm(g, pts, s, c=c, nthreads=2)
+        assert np.array_equal(got, want), c
+    py = O.multi_exp(G, G.decode_affine(pts), [O.Field.from_limbs(r) for r in s], c=11)
+    assert np.array_equal(G.encode_affine([py])[0], want)
