@@ -149,3 +149,28 @@ def test_resident_bases_precompute_matches_plain_and_closed_form(g, n, c):
             rb.Precompute(c)          # already built
     finally:
         rb.close()
+
+
+def test_sharded_resident_bases_with_tables(monkeypatch):
+    """bases sharded over the devices of GMSM_DEVICES (device = -1), here two shards on device 0 so that the path runs on a
+    one-GPU box: one host thread per shard, every shard returns ONE partial in window-table mode, joined on the first"""
+    mx = import_module("gnark-crypto_b200.multiexp")
+    g = "bn254_g1"
+    n = (1 << 17) + 5
+    pts, s = make_inputs(g, n, 12)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=8)
+    monkeypatch.setenv("GMSM_DEVICES", "0,0")
+    rb = mx.ResidentBases(g, pts, device=-1)
+    try:
+        w = pts.shape[1]
+        assert np.array_equal(rb.MultiExp(s)[:w], want)
+        assert rb.Precompute(0) >= 6
+        assert np.array_equal(rb.MultiExp(s)[:w], want)
+        lo, m = n // 5, n // 2                      # straddles the shard boundary
+        want_sub, _, _, _ = cref.msm(g, pts[lo : lo + m], s[:m], c=0, nthreads=8)
+        assert np.array_equal(rb.MultiExp(s[:m], offset=lo)[:w], want_sub)
+        m2 = n // 4                                 # inside the first shard only (single-job path)
+        want_one, _, _, _ = cref.msm(g, pts[3 : 3 + m2], s[:m2], c=0, nthreads=8)
+        assert np.array_equal(rb.MultiExp(s[:m2], offset=3)[:w], want_one)
+    finally:
+        rb.close()
