@@ -48,6 +48,7 @@ GMSM_D T load_vec_ro(const T* p) {
   static_assert(sizeof(T) % 16 == 0, "16-byte granules");
   T r;
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#if defined(__CUDA_ARCH__)
   if constexpr (sizeof(T) % 32 == 0) {
     const char* s = reinterpret_cast<const char*>(p);
 #pragma unroll
@@ -57,7 +58,9 @@ GMSM_D T load_vec_ro(const T* p) {
                      "=r"(w[8 * i + 5]), "=r"(w[8 * i + 6]), "=r"(w[8 * i + 7])
                    : "l"(s + 32 * i));
     }
-  } else {
+  } else
+#endif
+  {   // (also the whole function in the CPU emulation build of tests/emu/, which has no PTX)
     const uint4* s = reinterpret_cast<const uint4*>(p);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) {

@@ -1,0 +1,219 @@
+// TEST INFRASTRUCTURE ONLY -- runs the product's kernels (gnark-crypto_b200/csrc/kernels.cuh, unmodified) on the CPU, one
+// emulated thread at a time, in the order gnark-crypto_b200/csrc/engine_impl.cuh launches them (run_accumulate,
+// run_bucket_reduce, run_finalize), so that the kernel-level logic -- digit recoding + histogram, the two scatters,
+// the chunked segmented reduction with its owner / carry rule and the two-part launch, the carry levels, the
+// segment reduction, the finalize, the window-table level -- is checked against the oracle WITHOUT a GPU
+// (tests/test_emu_kernels.py).  Chunk length, carry run lengths, segment length, scatter passes and the launch
+// split are parameters here, so the tests also visit shapes the engine's own heuristics would not pick.
+// Never linked into libgmsm.so: the product has no CPU path.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace gmsm;
+
+namespace {
+
+struct Opts {
+  int c;
+  int tables;         // 1: window-table mode (one shared bucket set over W table rows)
+  uint32_t K;         // entries per accumulate chunk
+  uint32_t K2_first;  // items per thread, first carry level
+  uint32_t K2;        // ... later levels
+  uint32_t L;         // buckets per reduction segment
+  int passes;         // bucket-range passes of the shared scatter
+  int split;          // > 0: two-part accumulate, split after `split` windows / passes
+  int batches;        // > 1: pipelined batches (scratch buckets + k_merge_buckets)
+};
+
+static unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+// stages K1..K2b of engine_impl.cuh's run_accumulate on one batch: afterwards `buckets` holds the batch's bucket sums
+template <class G>
+int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, const typename G::Fr* scalars, size_t n, const WindowPlan& p,
+                   bool shared, const Opts& o, std::vector<XYZZ<typename G::F>>& buckets) {
+  using F = typename G::F;
+  using X = XYZZ<F>;
+  if (n == 0) return 0;
+  const uint32_t n32 = (uint32_t)n;
+  const size_t nbp = (size_t)p.nb_total + 1;
+    // K1: digits + histogram
+    std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), entries(n * (size_t)p.nwin + 16, 0);
+    emu_launch(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256, scalars, n32, p.c, p.nwin,
+               shared ? 0u : p.nb, digits.data(), hist.data());
+    // K1b: exclusive scan (the three scan kernels need warp shuffles: host scan here)
+    {
+      uint32_t run = 0;
+      for (size_t i = 0; i < nbp; i++) { offsets[i] = run; run += hist[i]; }
+    }
+    // K1c: scatter
+    int NPASS = p.nwin;
+    if (shared) NPASS = std::max(1, o.passes);
+    const uint32_t range_sz = shared ? (p.nb_total + (uint32_t)NPASS - 1) / (uint32_t)NPASS : p.nb;
+    if (shared) {
+      for (int r = 0; r < NPASS; r++) {
+        const uint32_t blo = (uint32_t)std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
+        const uint32_t bhi = (uint32_t)std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
+        if (blo >= bhi) continue;
+        emu_launch(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(), n32,
+                   row_stride, hist.data(), (const uint32_t*)offsets.data(), entries.data(), blo, bhi);
+      }
+    } else {
+      for (int j = 0; j < p.nwin; j++)
+        emu_launch(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n), n32,
+                   hist.data() + (size_t)j * p.nb, (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data());
+    }
+    for (size_t i = 0; i < nbp; i++)
+      if (hist[i] != 0) return 10;   // every counter must have been consumed exactly
+    // K2: accumulate
+    const uint32_t K = o.K;
+    const size_t nchunks = (n * (size_t)p.nwin + K - 1) / K;
+    std::vector<X> carr0(nchunks), carr1((nchunks + 1) / 2 + 1);
+    std::vector<uint32_t> ids0(nchunks + 8, 0), ids1((nchunks + 1) / 2 + 8, 0);
+    const int split = std::min(o.split, NPASS);
+    if (split > 0 && split < NPASS) {
+      const uint32_t split_bucket = (uint32_t)std::min<uint64_t>((uint64_t)split * range_sz, p.nb_total);
+      for (int part = 1; part <= 2; part++)
+        emu_launch(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
+                   p.nb_total, K, (uint32_t)nchunks, buckets.data(), carr0.data(), ids0.data(), part, split_bucket);
+    } else {
+      emu_launch(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
+                 p.nb_total, K, (uint32_t)nchunks, buckets.data(), carr0.data(), ids0.data(), 0, 0u);
+    }
+    // K2b: carry levels
+    {
+      size_t n_in = nchunks;
+      bool first = true;
+      X* cp[2] = {carr0.data(), carr1.data()};
+      uint32_t* ip[2] = {ids0.data(), ids1.data()};
+      std::vector<X> big1;
+      std::vector<uint32_t> bigi;
+      int cur = 0;
+      while (n_in > 1) {
+        const uint32_t k2 = first ? o.K2_first : o.K2;
+        first = false;
+        const size_t n_out = (n_in + k2 - 1) / k2;
+        emu_launch(k_carry_level<G>, dim3(nblk(n_out, 128)), 128, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2, buckets.data(),
+                   cp[cur ^ 1], ip[cur ^ 1]);
+        n_in = n_out;
+        cur ^= 1;
+      }
+    }
+  return 0;
+}
+
+template <class G>
+int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o, void* out_jac) {
+  using F = typename G::F;
+  using X = XYZZ<F>;
+  using A = Affine<F>;
+  WindowPlan p = make_plan(G::FrParams::BITS, o.c);
+  const bool shared = o.tables != 0;
+  if (shared) p.nb_total = std::max(p.nb, p.nb_last);
+  const int red_windows = shared ? 1 : p.nwin;
+  const uint32_t n32 = (uint32_t)n;
+  const auto* scalars = reinterpret_cast<const typename G::Fr*>(scalars_v);
+  const A* points = reinterpret_cast<const A*>(points_v);
+
+  // window tables: row j = 2^c * row j-1 (gmsm_tables_build_device)
+  std::vector<A> table;
+  if (shared) {
+    table.resize((size_t)p.nwin * std::max<size_t>(n, 1));
+    if (n) std::memcpy(table.data(), points, n * sizeof(A));
+    for (int j = 1; j < p.nwin && n; j++)
+      emu_launch(k_table_level<G>, dim3(nblk((n + TAB_M - 1) / TAB_M, 128)), 128, (const A*)(table.data() + (size_t)(j - 1) * n), n32, o.c,
+                 table.data() + (size_t)j * n);
+    points = table.data();
+  }
+
+  std::vector<X> buckets(p.nb_total, X::inf());
+  std::vector<X> partials(red_windows, X::inf());
+  // pipelined host calls (pipeline_run in gmsm.cu): contiguous batches, the first into the bucket array, every later
+  // one into scratch buckets that k_merge_buckets adds on top
+  const int nbatch = std::max(1, std::min<int>(o.batches, (int)std::max<size_t>(n, 1)));
+  for (int bi = 0; bi < nbatch; bi++) {
+    const size_t lo = n * bi / nbatch, hi = n * (bi + 1) / nbatch;
+    if (bi == 0) {
+      if (int rc = emu_accumulate<G>(points + lo, (uint32_t)n, scalars + lo, hi - lo, p, shared, o, buckets)) return rc;
+    } else {
+      std::vector<X> scratch_b(p.nb_total, X::inf());
+      if (int rc = emu_accumulate<G>(points + lo, (uint32_t)n, scalars + lo, hi - lo, p, shared, o, scratch_b)) return rc;
+      emu_launch(k_merge_buckets<G>, dim3(nblk(p.nb_total, 128)), 128, buckets.data(), (const X*)scratch_b.data(), p.nb_total);
+    }
+  }
+  // K3: bucket reduction
+  {
+    const uint32_t nbmax = shared ? p.nb_total : std::max(p.nb, p.nb_last);
+    const uint32_t L = o.L, S = (nbmax + L - 1) / L;
+    const uint32_t nb_reg = shared ? p.nb_total : p.nb, nb_last = shared ? p.nb_total : p.nb_last;
+    std::vector<X> seg0((size_t)red_windows * S), seg1((size_t)red_windows * ((S + 15) / 16) + 1);
+    emu_launch(k_bucket_segments<G>, dim3(nblk((size_t)red_windows * S, 128)), 128, (const X*)buckets.data(), red_windows, nb_reg, nb_last, L, S,
+               seg0.data());
+    uint32_t per = S;
+    X* sp[2] = {seg0.data(), seg1.data()};
+    int cur = 0;
+    while (per > 1) {
+      const uint32_t R = 16, outp = (per + R - 1) / R;
+      X* dst = (outp == 1) ? partials.data() : sp[cur ^ 1];
+      emu_launch(k_sum_groups<G>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
+      per = outp;
+      cur ^= 1;
+    }
+    if (S == 1) std::memcpy(partials.data(), seg0.data(), (size_t)red_windows * sizeof(X));
+  }
+  // K4: finalize
+  std::vector<X> scratch(red_windows);
+  Jac<F> out;
+  emu_launch(k_finalize<G>, dim3(1), 32, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  std::memcpy(out_jac, &out, sizeof(out));
+  return 0;
+}
+
+}  // namespace
+
+#ifndef EMU_GROUP
+#error "compile with -DEMU_GROUP=0..5"
+#endif
+#if EMU_GROUP == 0
+using EmuG = bn254_g1;
+#elif EMU_GROUP == 1
+using EmuG = bn254_g2;
+#elif EMU_GROUP == 2
+using EmuG = bls12381_g1;
+#elif EMU_GROUP == 3
+using EmuG = bls12381_g2;
+#elif EMU_GROUP == 4
+using EmuG = bls12377_g1;
+#else
+using EmuG = bls12377_g2;
+#endif
+#define EMU_CAT2(a, b) a##b
+#define EMU_CAT(a, b) EMU_CAT2(a, b)
+extern "C" int EMU_CAT(emu_msm_, EMU_GROUP)(const void* points, const void* scalars, size_t n, int c, int tables, uint32_t K, uint32_t K2_first,
+                                             uint32_t K2, uint32_t L, int passes, int split, int batches, void* out_jac) {
+  if (c < 2 || c > 24 || K < 1 || K2_first < 2 || K2 < 2 || L < 1) return 1;
+  Opts o{c, tables, K, K2_first, K2, L, passes, split, batches};
+  return emu_msm<EmuG>(points, scalars, n, o, out_jac);
+}
+
+// fixed-base helpers: k_generate_multiples (out[i] = [start + i] * base) and k_batch_scalar_mul (N1,
+// BatchScalarMultiplicationG1/G2, g1.go:1039-1118) as gmsm_batch_scalar_mul launches them
+extern "C" int EMU_CAT(emu_generate_, EMU_GROUP)(const void* base, uint64_t start, size_t n, void* out) {
+  using A = Affine<typename EmuG::F>;
+  if (n == 0) return 0;
+  emu_launch(k_generate_multiples<EmuG>, dim3(nblk((n + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, start, (uint64_t)n, (A*)out);
+  return 0;
+}
+extern "C" int EMU_CAT(emu_batch_scalar_mul_, EMU_GROUP)(const void* base, const void* scalars, size_t n, int c, void* out) {
+  using A = Affine<typename EmuG::F>;
+  if (n == 0) return 0;
+  const WindowPlan p = make_plan(EmuG::FrParams::BITS, c);
+  const size_t tbl = (size_t)1 << (std::max(p.c, p.last_c) - 1);
+  std::vector<A> table(tbl);
+  emu_launch(k_generate_multiples<EmuG>, dim3(nblk((tbl + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, (uint64_t)1, (uint64_t)tbl, table.data());
+  emu_launch(k_batch_scalar_mul<EmuG>, dim3(nblk(n, 128)), 128, (const A*)table.data(), (const typename EmuG::Fr*)scalars, (uint32_t)n, p.c, p.nwin,
+             (A*)out);
+  return 0;
+}

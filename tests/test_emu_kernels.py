@@ -1,0 +1,168 @@
+"""The product's CUDA kernels (gnark-crypto_b200/csrc/kernels.cuh, the file nvcc compiles) run on the CPU, one emulated
+thread at a time, in the engine's launch order (tests/emu/emu_engine.cpp over the stand-in tests/emu/cuda_runtime.h), and
+compared with the oracle.  This checks the kernel-level logic without a GPU: digit recoding + histogram, the per-window
+and the shared (window-table) scatter, the chunked segmented reduction with its owner / carry rule and the two-part
+launch, the carry levels, the segment reduction, the finalize and the table level -- at chunk lengths, carry run
+lengths, segment lengths and pass counts the engine's own heuristics would not pick.  The device arithmetic itself
+(PTX carry chains) is covered by tests/test_hostcheck.py; the real launches by the -m gpu tests.  Threads run one after
+the other, so this finds logic errors, not data races (compute-sanitizer racecheck on the GPU does that:
+profiles/r01_compute_sanitizer_racecheck.log).  CPU only; a test artefact (build/libgmsm_emu.so), never part of libgmsm.so."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cref
+from oracle import oracle as O
+from tests.gpu_common import load_golden_msm, make_inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "gnark-crypto_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+OUT = os.path.join(ROOT, "gnark-crypto_b200", "build", "libgmsm_emu.so")
+GROUPS = list(O.GROUPS)
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        bdir = os.path.dirname(OUT)
+        os.makedirs(bdir, exist_ok=True)
+        deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [
+            os.path.join(EMU, f) for f in os.listdir(EMU)]
+        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in deps):
+            objs, procs = [], []
+            for k in range(6):
+                o = os.path.join(bdir, "emu_%d.o" % k)
+                objs.append(o)
+                # tests/emu FIRST: its cuda_runtime.h stands in for the real one
+                procs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-fPIC", "-DEMU_GROUP=%d" % k, "-I", EMU, "-I", CSRC, "-c",
+                                               os.path.join(EMU, "emu_engine.cpp"), "-o", o]))
+            assert all(p.wait() == 0 for p in procs)
+            subprocess.run(["g++", "-shared", "-o", OUT, *objs], check=True)
+        _LIB = ctypes.CDLL(OUT)
+    return _LIB
+
+
+def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, split=0, batches=1):
+    pts = np.ascontiguousarray(pts, dtype=np.uint64)
+    s = np.ascontiguousarray(s, dtype=np.uint64)
+    w = pts.shape[1] // 2
+    out = np.zeros(3 * w, dtype=np.uint64)
+    fn = getattr(_lib(), "emu_msm_%d" % GROUPS.index(g))
+    rc = fn(pts.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(pts.shape[0]), c, tables,
+            K, K2_first, K2, L, passes, split, batches, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, rc
+    return out
+
+
+def _check(g, jac, want):
+    G = O.GROUPS[g]
+    w = want.size // 2
+    assert np.array_equal(jac[: 2 * w], want)
+    one = np.array(G.K.encode(G.K.one), dtype=np.uint64)
+    assert np.array_equal(jac[2 * w :], one if want.any() else np.zeros_like(one))
+
+
+@pytest.mark.parametrize("g", GROUPS)
+def test_emulated_kernels_match_golden_vectors(g):
+    """committed known answers through the emulated kernel pipeline: plain and window-table mode, several widths"""
+    pts, s, want = load_golden_msm(g)
+    for c, tables in ((4, 0), (9, 0), (16, 0), (5, 1), (11, 1)):
+        _check(g, emu_msm(g, pts, s, c, tables=tables, K=8, split=2 if c < 16 else 0), want)
+
+
+@pytest.mark.parametrize("tables", [0, 1])
+def test_emulated_kernels_shapes_bn254_g1(tables):
+    """chunk lengths from 1 (every entry its own chunk) to longer than any bucket, short and long carry runs, segment
+    lengths, pass counts, with and without the two-part accumulate"""
+    g = "bn254_g1"
+    pts, s = make_inputs(g, 1500, 321)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c in (3, 8, 13):
+        for K, K2f, K2, L, passes, split in ((1, 2, 2, 1, 1, 0), (3, 4, 16, 7, 3, 1), (16, 4, 16, 32, 4, 2), (256, 16, 16, 64, 12, 5),
+                                             (5000, 3, 5, 1000, 2, 1)):
+            _check(g, emu_msm(g, pts, s, c, tables=tables, K=K, K2_first=K2f, K2=K2, L=L, passes=passes, split=split), want)
+
+
+@pytest.mark.parametrize("kind", ["smallvalues", "redundancy", "one_bucket", "all_equal_points", "all_infinity", "zero_scalars", "empty", "single"])
+@pytest.mark.parametrize("tables", [0, 1])
+def test_emulated_kernels_skewed_inputs(kind, tables):
+    """the distributions of multiexp_test.go:319-334 and harder ones: buckets that span many chunks go through several
+    carry levels; all-equal points take the doubling branch; empty and one-element inputs"""
+    g = "bn254_g1"
+    n = 900
+    pts, s = make_inputs(g, n, 55, specials=False)
+    if kind == "smallvalues":
+        s[::5] = np.array([1, 0, 0, 0], dtype=np.uint64)
+    elif kind == "redundancy":
+        for i in range(0, n, 100):
+            s[i : i + 100] = s[i]
+    elif kind == "one_bucket":
+        s[:] = s[0]
+    elif kind == "all_equal_points":
+        pts[:] = pts[3]
+    elif kind == "all_infinity":
+        pts[:] = 0
+    elif kind == "zero_scalars":
+        s[:] = 0
+    elif kind == "empty":
+        pts, s = pts[:0], s[:0]
+    else:
+        pts, s = pts[7:8], s[7:8]
+    if pts.shape[0]:
+        want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    else:
+        want = np.zeros(8, dtype=np.uint64)
+    for c, K, split in ((6, 4, 0), (12, 16, 2)):
+        _check(g, emu_msm(g, pts, s, c, tables=tables, K=K, K2_first=4, K2=4, split=split), want)
+
+
+@pytest.mark.parametrize("g,n", [("bn254_g2", 300), ("bls12381_g1", 400), ("bls12381_g2", 150), ("bls12377_g1", 300), ("bls12377_g2", 120)])
+def test_emulated_kernels_other_groups(g, n):
+    pts, s = make_inputs(g, n, 99)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    _check(g, emu_msm(g, pts, s, 7, tables=0, K=8, split=3), want)
+    _check(g, emu_msm(g, pts, s, 10, tables=1, K=32, passes=3, split=1), want)
+
+
+@pytest.mark.parametrize("tables", [0, 1])
+def test_emulated_pipelined_batches(tables):
+    """the host calls cut large inputs into batches that share one bucket array (gmsm.cu pipeline_run): later batches go
+    to scratch buckets and k_merge_buckets adds them on top; in window-table mode the batch's points are a sub-range of
+    every table row"""
+    g = "bn254_g1"
+    pts, s = make_inputs(g, 1100, 77)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c, batches in ((7, 2), (11, 5)):
+        _check(g, emu_msm(g, pts, s, c, tables=tables, K=8, batches=batches, split=1), want)
+
+
+@pytest.mark.parametrize("g", ["bn254_g1", "bn254_g2", "bls12381_g1"])
+def test_emulated_fixed_base_kernels(g):
+    """k_generate_multiples and k_batch_scalar_mul (next-row N1: BatchScalarMultiplicationG1/G2, g1.go:1039-1118)"""
+    G = O.GROUPS[g]
+    lib = _lib()
+    k = GROUPS.index(g)
+    base = G.encode_affine([G.scalar_mul(G.gen, 0xBEEF)])[0]
+    w = base.size
+    n = 77
+    out = np.zeros((n, w), dtype=np.uint64)
+    vp = ctypes.c_void_p
+    assert getattr(lib, "emu_generate_%d" % k)(base.ctypes.data_as(vp), ctypes.c_uint64(5), ctypes.c_size_t(n), out.ctypes.data_as(vp)) == 0
+    for i in (0, 1, 15, 16, 17, 76):
+        assert np.array_equal(out[i], cref.scalar_mul(g, base, 5 + i)), i
+    s = cref.random_scalars(g, 40, 9)
+    specials = [0, 1, 2, G.fr.q - 1, (1 << 200) + 12345]
+    s[: len(specials)] = G.encode_scalars(specials)
+    ks = G.decode_scalars(s)
+    for c in (4, 8):
+        got = np.zeros((40, w), dtype=np.uint64)
+        assert getattr(lib, "emu_batch_scalar_mul_%d" % k)(base.ctypes.data_as(vp), s.ctypes.data_as(vp), ctypes.c_size_t(40), c,
+                                                           got.ctypes.data_as(vp)) == 0
+        for i in range(40):
+            assert np.array_equal(got[i], cref.scalar_mul(g, base, ks[i])), (c, i)
+        assert not got[0].any() and np.array_equal(got[1], base)
