@@ -119,6 +119,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def int_pipe_fraction(g, mixed_adds_per_s, sm_mhz):
+    """The binding unit of the bucket pass is the INT32 multiplier: one mixed addition is 8 M + 2 S in
+    the coordinate field = 10 Fp multiplications for G1, 28 for G2 (Fp2: M = 3, S = 2 Fp multiplications), each 2N^2 + N
+    IMAD.WIDE (N 32-bit limbs); an SM sub-partition issues one IMAD.WIDE warp-instruction every 4 cycles: 148 SMs x 32
+    wide MADs per clock.  Returns {"wide_mads_per_s", "peak", "frac"}, or None if the clock is unknown."""
+    try:
+        limbs = AFF_BYTES[g] // (16 if g.endswith("g2") else 8)        # 32-bit limbs of one Fp element
+        fp_muls = 28 if g.endswith("g2") else 10
+        per_add = fp_muls * (2 * limbs * limbs + limbs)
+        peak = 148 * 32 * float(sm_mhz) * 1e6
+        ach = float(mixed_adds_per_s) * per_add
+        return {"wide_mads_per_mixed_add": per_add, "wide_mads_per_s": ach, "peak": peak, "frac": ach / peak,
+                "peak_source": "148 SMs x 32 IMAD.WIDE/clk at the sampled SM clock"}
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -298,6 +315,8 @@ def main():
                 "int_pipe": {"mixed_adds_per_s": n * W / (acc * 1e-3), "note": "INT32-pipe bound: ~10 modmul (~1.4k IMAD.WIDE) per 66 B"}}
     stage_names = ["digits_hist", "scan", "scatter", "accumulate", "carries", "bucket_reduce", "finalize", "total"]
 
+    if clocks and clocks.get("sm_mhz"):
+        roofline["int_pipe"]["multiplier_pipe"] = int_pipe_fraction(g, n * W / (acc * 1e-3), clocks["sm_mhz"])
     line = {
         "metric": "bn254 G1 MultiExp scalar-muls/s" if g == "bn254_g1" else g + " MultiExp scalar-muls/s",
         "value": value, "unit": "scalar-muls/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
