@@ -166,3 +166,41 @@ def test_emulated_fixed_base_kernels(g):
         for i in range(40):
             assert np.array_equal(got[i], cref.scalar_mul(g, base, ks[i])), (c, i)
         assert not got[0].any() and np.array_equal(got[1], base)
+
+
+def test_emulated_kernels_randomised_shapes():
+    """seeded sweep over sizes, widths, chunk / run / segment lengths, pass counts, launch splits, batch counts, both modes
+    and input mixes (infinity points, zero / tiny / repeated scalars, duplicated and negated points): whatever the shape,
+    the kernel pipeline must reproduce the reference algorithm's result"""
+    import random
+
+    g = "bn254_g1"
+    G = O.GROUPS[g]
+    base_pts, base_s = make_inputs(g, 320, 4242, specials=False)
+    rng = random.Random(20260923)
+    for it in range(160):
+        n = rng.choice([1, 2, 3, 5, 17, 31, 32, 33, 64, 100, 127, 200, 257, 320])
+        pts, s = base_pts[:n].copy(), base_s[:n].copy()
+        for _ in range(rng.randrange(0, 4)):                       # input mix
+            kind = rng.randrange(6)
+            i, j = rng.randrange(n), rng.randrange(n)
+            if kind == 0:
+                pts[i] = 0
+            elif kind == 1:
+                s[i] = 0
+            elif kind == 2:
+                s[i] = np.array([rng.randrange(1, 9), 0, 0, 0], dtype=np.uint64)
+            elif kind == 3:
+                s[min(i, j) : max(i, j) + 1] = s[i]
+            elif kind == 4:
+                pts[i], s[i] = pts[j], s[j]
+            else:
+                pts[i] = G.encode_affine([G.aff_neg(G.decode_affine(pts[j : j + 1])[0])])[0]
+                s[i] = s[j]
+        c = rng.randrange(2, 17)
+        opt = dict(tables=rng.randrange(2), K=rng.choice([1, 2, 3, 4, 7, 8, 16, 33, 64, 1000]), K2_first=rng.randrange(2, 9),
+                   K2=rng.randrange(2, 17), L=rng.choice([1, 2, 3, 8, 32, 64, 100]), passes=rng.randrange(1, 9),
+                   split=rng.randrange(0, 7), batches=rng.choice([1, 1, 2, 3]))
+        want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=2)
+        jac = emu_msm(g, pts, s, c, **opt)
+        assert np.array_equal(jac[:8], want), (it, n, c, opt)
