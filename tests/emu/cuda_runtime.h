@@ -45,17 +45,30 @@ static inline uint32_t __shfl_up_sync(uint32_t, uint32_t, int) {
 }
 
 // emulated launch: every thread of every block in turn; lanes in DESCENDING order inside a block, so that the
-// "lane 0 continues after the barrier" pattern of k_finalize sees the other lanes' work
+// "lane 0 continues after the barrier" pattern of k_finalize sees the other lanes' work.  A GPU runs blocks in no
+// particular order (which decides, e.g., the order of the entries inside a bucket after the atomic scatter):
+// emu_block_order = 0 ascending, 1 descending, >= 2 a pseudo-random permutation seeded by it.
+inline unsigned emu_block_order = 0;
 template <class K, class... A>
 static inline void emu_launch(K kernel, dim3 grid, unsigned block, A... args) {
   gridDim = grid;
   blockDim = dim3(block);
-  for (unsigned by = 0; by < grid.y; by++)
-    for (unsigned bx = 0; bx < grid.x; bx++) {
-      blockIdx = dim3(bx, by, 0);
-      for (unsigned t = block; t-- > 0;) {
-        threadIdx = dim3(t, 0, 0);
-        kernel(args...);
-      }
+  const uint64_t nb = (uint64_t)grid.x * grid.y;
+  // permutation i -> (a*i + b) mod nb with gcd(a, nb) = 1
+  uint64_t a = 1, b = 0;
+  if (emu_block_order == 1) { a = nb - 1 ? nb - 1 : 1; b = nb - 1; }
+  if (emu_block_order >= 2 && nb > 2) {
+    a = (0x9E3779B97F4A7C15ull * emu_block_order) % nb;
+    auto gcd = [](uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; };
+    while (a == 0 || gcd(a, nb) != 1) a = (a + 1) % nb;
+    b = (0xD1B54A32D192ED03ull * emu_block_order) % nb;
+  }
+  for (uint64_t i = 0; i < nb; i++) {
+    const uint64_t k = (a * i + b) % nb;
+    blockIdx = dim3((unsigned)(k % grid.x), (unsigned)(k / grid.x), 0);
+    for (unsigned t = block; t-- > 0;) {
+      threadIdx = dim3(t, 0, 0);
+      kernel(args...);
     }
+  }
 }

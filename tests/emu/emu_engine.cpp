@@ -217,3 +217,5 @@ extern "C" int EMU_CAT(emu_batch_scalar_mul_, EMU_GROUP)(const void* base, const
              (A*)out);
   return 0;
 }
+
+extern "C" void EMU_CAT(emu_set_block_order_, EMU_GROUP)(unsigned order) { emu_block_order = order; }

@@ -47,7 +47,9 @@ def _lib():
     return _LIB
 
 
-def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, split=0, batches=1):
+def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, split=0, batches=1, order=0):
+    """order: block execution order of every emulated launch (0 ascending, 1 descending, >= 2 pseudo-random)"""
+    getattr(_lib(), "emu_set_block_order_%d" % GROUPS.index(g))(order)
     pts = np.ascontiguousarray(pts, dtype=np.uint64)
     s = np.ascontiguousarray(s, dtype=np.uint64)
     w = pts.shape[1] // 2
@@ -200,7 +202,18 @@ def test_emulated_kernels_randomised_shapes():
         c = rng.randrange(2, 17)
         opt = dict(tables=rng.randrange(2), K=rng.choice([1, 2, 3, 4, 7, 8, 16, 33, 64, 1000]), K2_first=rng.randrange(2, 9),
                    K2=rng.randrange(2, 17), L=rng.choice([1, 2, 3, 8, 32, 64, 100]), passes=rng.randrange(1, 9),
-                   split=rng.randrange(0, 7), batches=rng.choice([1, 1, 2, 3]))
+                   split=rng.randrange(0, 7), batches=rng.choice([1, 1, 2, 3]), order=rng.choice([0, 1, 2, 3, 7, 12345]))
         want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=2)
         jac = emu_msm(g, pts, s, c, **opt)
         assert np.array_equal(jac[:8], want), (it, n, c, opt)
+
+
+@pytest.mark.parametrize("g,n", [("bn254_g2", 90), ("bls12381_g1", 120)])
+def test_emulated_kernels_block_order_independent(g, n):
+    """a GPU runs the blocks of a launch in no particular order, which changes the order of the entries inside a bucket
+    (atomic scatter) and with it the chain of additions: the affine normal form of the result must not depend on it"""
+    pts, s = make_inputs(g, n, 31)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for order in (0, 1, 2, 5, 99):
+        for tables in (0, 1):
+            _check(g, emu_msm(g, pts, s, 6, tables=tables, K=4, passes=2, split=1, order=order), want)
