@@ -8,9 +8,15 @@
 // __funnelshift_r, __syncthreads (a no-op: kernels that NEED a barrier or warp shuffles -- the three scan kernels --
 // are not run; the emulated engine scans on the host instead; k_finalize only needs lane 0 to run last).
 #pragma once
+#include <ucontext.h>
+
+#include <algorithm>
 #include <cassert>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <functional>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -38,10 +44,82 @@ static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
 }
-static inline void __syncthreads() {}
-static inline uint32_t __shfl_up_sync(uint32_t, uint32_t, int) {
-  assert(!"warp shuffles are not emulated: the scan kernels are replaced by a host scan");
-  return 0;
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = std::max(o, v); return o; }
+using std::max;
+using std::min;
+#define __align__(n) __attribute__((aligned(n)))
+
+// ---- cooperative blocks: one fiber (ucontext) per CUDA thread, so that __syncthreads and warp shuffles work -------
+// emu_launch_coop runs ONE block at a time; a fiber runs until it blocks in a barrier / shuffle or returns; a barrier
+// opens when every live thread of the block (of the warp) has arrived -- exited threads count as arrived, as on the
+// hardware.  `__shared__` variables (static thread_local here) are shared by the fibers of the running block.
+namespace emu {
+struct Block {
+  unsigned nthreads = 0, live = 0;
+  std::vector<ucontext_t> ctx;
+  std::vector<char*> stacks;
+  std::vector<char> done;
+  ucontext_t sched;
+  unsigned cur = 0;
+  unsigned bar_arrived = 0, bar_gen = 0;
+  unsigned warp_live[32] = {}, warp_arrived[32] = {}, warp_gen[32] = {};
+  uint32_t slot[1024] = {};
+  std::function<void()> body;
+};
+inline Block* g_block = nullptr;   // non-null while a cooperative launch is running
+inline void yield() {
+  Block& B = *g_block;
+  swapcontext(&B.ctx[B.cur], &B.sched);
+}
+inline void block_barrier() {
+  Block& B = *g_block;
+  const unsigned gen = B.bar_gen;
+  if (++B.bar_arrived >= B.live) { B.bar_arrived = 0; B.bar_gen++; return; }
+  while (B.bar_gen == gen) yield();
+}
+inline void warp_barrier() {
+  Block& B = *g_block;
+  const unsigned w = B.cur >> 5, gen = B.warp_gen[w];
+  if (++B.warp_arrived[w] >= B.warp_live[w]) { B.warp_arrived[w] = 0; B.warp_gen[w]++; return; }
+  while (B.warp_gen[w] == gen) yield();
+}
+inline void thread_exit() {   // an exiting thread may complete a barrier the others are waiting in
+  Block& B = *g_block;
+  const unsigned w = B.cur >> 5;
+  B.done[B.cur] = 1;
+  B.live--;
+  B.warp_live[w]--;
+  if (B.live && B.bar_arrived >= B.live) { B.bar_arrived = 0; B.bar_gen++; }
+  if (B.warp_live[w] && B.warp_arrived[w] >= B.warp_live[w]) { B.warp_arrived[w] = 0; B.warp_gen[w]++; }
+}
+inline void trampoline() {
+  g_block->body();
+  thread_exit();
+  yield();   // never resumed
+}
+inline uint32_t shfl(uint32_t v, unsigned src_lane, bool valid) {
+  Block& B = *g_block;
+  const unsigned tid = B.cur, base = tid & ~31u;
+  B.slot[tid] = v;
+  warp_barrier();
+  const uint32_t r = (valid && base + src_lane < B.nthreads) ? B.slot[base + src_lane] : v;
+  warp_barrier();
+  return r;
+}
+}  // namespace emu
+
+static inline void __syncthreads() {
+  if (emu::g_block) emu::block_barrier();   // sequential launches (emu_launch): no-op, see there
+}
+static inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, int delta) {
+  assert(emu::g_block && "warp shuffles need emu_launch_coop");
+  const unsigned lane = emu::g_block->cur & 31u;
+  return emu::shfl(v, lane - (unsigned)delta, lane >= (unsigned)delta);
+}
+static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, int mask) {
+  assert(emu::g_block && "warp shuffles need emu_launch_coop");
+  const unsigned lane = emu::g_block->cur & 31u;
+  return emu::shfl(v, lane ^ (unsigned)mask, true);
 }
 
 // emulated launch: every thread of every block in turn; lanes in DESCENDING order inside a block, so that the
@@ -71,4 +149,46 @@ static inline void emu_launch(K kernel, dim3 grid, unsigned block, A... args) {
       kernel(args...);
     }
   }
+}
+
+// cooperative launch: fibers, blocks one after the other (in emu_block_order), threads of a block interleaved at barriers
+template <class K, class... A>
+static inline void emu_launch_coop(K kernel, dim3 grid, unsigned block, A... args) {
+  gridDim = grid;
+  blockDim = dim3(block);
+  const uint64_t nb = (uint64_t)grid.x * grid.y;
+  constexpr size_t STACK = 512 * 1024;
+  emu::Block B;
+  B.nthreads = block;
+  B.ctx.resize(block);
+  B.stacks.resize(block, nullptr);
+  B.done.resize(block);
+  for (unsigned t = 0; t < block; t++) B.stacks[t] = (char*)std::malloc(STACK);
+  B.body = [&]() { kernel(args...); };
+  for (uint64_t i = 0; i < nb; i++) {
+    const uint64_t k = (emu_block_order == 1) ? nb - 1 - i : i;
+    blockIdx = dim3((unsigned)(k % grid.x), (unsigned)(k / grid.x), 0);
+    B.live = block;
+    B.bar_arrived = 0;
+    for (unsigned w = 0; w < 32; w++) { B.warp_arrived[w] = 0; B.warp_live[w] = (block > w * 32) ? std::min(32u, block - w * 32) : 0; }
+    for (unsigned t = 0; t < block; t++) {
+      B.done[t] = 0;
+      getcontext(&B.ctx[t]);
+      B.ctx[t].uc_stack.ss_sp = B.stacks[t];
+      B.ctx[t].uc_stack.ss_size = STACK;
+      B.ctx[t].uc_link = nullptr;
+      makecontext(&B.ctx[t], (void (*)())emu::trampoline, 0);
+    }
+    emu::g_block = &B;
+    while (B.live) {
+      for (unsigned t = 0; t < block; t++) {
+        if (B.done[t]) continue;
+        B.cur = t;
+        threadIdx = dim3(t, 0, 0);
+        swapcontext(&B.sched, &B.ctx[t]);
+      }
+    }
+    emu::g_block = nullptr;
+  }
+  for (unsigned t = 0; t < block; t++) std::free(B.stacks[t]);
 }

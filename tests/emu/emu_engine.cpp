@@ -10,7 +10,7 @@
 #include <cstring>
 #include <vector>
 
-#include "kernels.cuh"
+#include "affine_kernels.cuh"
 
 using namespace gmsm;
 
@@ -26,7 +26,29 @@ struct Opts {
   int passes;         // bucket-range passes of the shared scatter
   int split;          // > 0: two-part accumulate, split after `split` windows / passes
   int batches;        // > 1: pipelined batches (scratch buckets + k_merge_buckets)
+  int mode;           // bit 0: the real K1b scan kernels (block scans with warp shuffles) instead of a host scan
+                      // bit 1: batch-affine bucket accumulation (affine_kernels.cuh, GMSM_AFFINE=1) instead of k_accumulate
+                      // bit 2: every launch through the cooperative (fiber) launcher
 };
+
+static bool g_coop_all = false;
+// launch through the sequential launcher, or the cooperative one when asked for (kernels with barriers / shuffles
+// always name emu_launch_coop directly)
+template <class Kn, class... A>
+static void LAUNCH(Kn kernel, dim3 grid, unsigned block, A... args) {
+  if (g_coop_all) emu_launch_coop(kernel, grid, block, args...);
+  else emu_launch(kernel, grid, block, args...);
+}
+
+// K1b as engine_impl.cuh's scan_u32: per-block totals, one-block scan of the totals, per-block scan + prefix
+static void real_scan(const uint32_t* in, uint32_t nbp, uint32_t* out) {
+  const unsigned nb_blocks = (unsigned)((nbp + SCAN_TILE - 1) / SCAN_TILE);
+  std::vector<uint32_t> block_sums(2 * (size_t)nb_blocks + 16, 0);
+  emu_launch_coop(k_scan_block_sums, dim3(nb_blocks), (unsigned)SCAN_THREADS, in, nbp, block_sums.data());
+  emu_launch_coop(k_scan_top, dim3(1), 1024u, block_sums.data(), (uint32_t)nb_blocks, block_sums.data() + nb_blocks);
+  emu_launch_coop(k_scan_final, dim3(nb_blocks), (unsigned)SCAN_THREADS, in, nbp, (const uint32_t*)block_sums.data(), out);
+}
+
 
 static unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
@@ -41,13 +63,15 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
   const size_t nbp = (size_t)p.nb_total + 1;
     // K1: digits + histogram
     std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), entries(n * (size_t)p.nwin + 16, 0);
-    emu_launch(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256, scalars, n32, p.c, p.nwin,
+    LAUNCH(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256, scalars, n32, p.c, p.nwin,
                shared ? 0u : p.nb, digits.data(), hist.data());
-    // K1b: exclusive scan (the three scan kernels need warp shuffles: host scan here)
-    {
+    // K1b: exclusive scan -- the three scan kernels (cooperative launch) or a host scan
+    auto scan_u32 = [&](const uint32_t* in, uint32_t* out) {
+      if (o.mode & 1) { real_scan(in, (uint32_t)nbp, out); return; }
       uint32_t run = 0;
-      for (size_t i = 0; i < nbp; i++) { offsets[i] = run; run += hist[i]; }
-    }
+      for (size_t i = 0; i < nbp; i++) { out[i] = run; run += in[i]; }
+    };
+    scan_u32(hist.data(), offsets.data());
     // K1c: scatter
     int NPASS = p.nwin;
     if (shared) NPASS = std::max(1, o.passes);
@@ -57,16 +81,73 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
         const uint32_t blo = (uint32_t)std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
         const uint32_t bhi = (uint32_t)std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
         if (blo >= bhi) continue;
-        emu_launch(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(), n32,
+        LAUNCH(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(), n32,
                    row_stride, hist.data(), (const uint32_t*)offsets.data(), entries.data(), blo, bhi);
       }
     } else {
       for (int j = 0; j < p.nwin; j++)
-        emu_launch(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n), n32,
+        LAUNCH(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n), n32,
                    hist.data() + (size_t)j * p.nb, (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data());
     }
     for (size_t i = 0; i < nbp; i++)
       if (hist[i] != 0) return 10;   // every counter must have been consumed exactly
+    if (o.mode & 2) {
+      // K2 (batch-affine, engine_impl.cuh's affine branch): balanced tree over the bucket-ordered entries, one shared
+      // inversion per level through the hierarchical product scans
+      using A = Affine<F>;
+      const uint32_t nbt = p.nb_total;
+      uint32_t maxlen = 0;
+      emu_launch_coop(k_aff_max_len, dim3(4), 256u, (const uint32_t*)offsets.data(), nbt, &maxlen);
+      int nlevels = 0;
+      while (((uint64_t)1 << nlevels) < maxlen) nlevels++;
+      const size_t ent = n * (size_t)p.nwin;
+      const size_t m1 = (ent + std::min(nbp, ent)) / 2 + 2, m2 = (m1 + std::min(nbp, m1)) / 2 + 2;
+      std::vector<A> buf0(m1), buf1(m2);
+      std::vector<F> pref(m1);
+      std::vector<uint32_t> off_a(nbp + 8, 0), off_b(nbp + 8, 0), counts(nbp + 8, 0);
+      const uint32_t* off_cur = offsets.data();
+      const A* src_cur = nullptr;
+      size_t m_up = ent;
+      for (int l = 0; l < nlevels; l++) {
+        uint32_t* off_next = (l & 1) ? off_b.data() : off_a.data();
+        LAUNCH(k_aff_level_counts, dim3(std::min<unsigned>(nblk(nbp, 256), 8u)), 256u, (const uint32_t*)offsets.data(), nbt, l + 1, counts.data());
+        scan_u32(counts.data(), off_next);
+        const size_t m_next = std::min(m_up, (m_up + std::min<size_t>(nbt, m_up)) / 2 + 1);
+        const uint32_t B = o.K ? std::min<uint32_t>(o.K, 128u) : 8u;      // slots per lane: the chunk-length knob
+        const size_t T = ((m_next + 32 * (size_t)B - 1) / (32 * (size_t)B)) * 32;
+        if (m_next > ((l & 1) ? m2 : m1)) return 11;
+        A* dst = (l & 1) ? buf1.data() : buf0.data();
+        std::vector<F> totals(T), ps(T);
+        const unsigned NB = nblk(T, PSCAN_TILE);
+        std::vector<F> bp(3 * ((size_t)NB + 8));
+        const size_t bp_stride = (size_t)NB + 8;
+        if (l == 0)
+          LAUNCH(k_aff_forward<G, true>, dim3(nblk(T, 128)), 128u, points, (const uint32_t*)entries.data(), src_cur, off_cur, (const uint32_t*)off_next,
+                 nbt, B, (uint32_t)T, pref.data(), totals.data());
+        else
+          LAUNCH(k_aff_forward<G, false>, dim3(nblk(T, 128)), 128u, points, (const uint32_t*)entries.data(), src_cur, off_cur, (const uint32_t*)off_next,
+                 nbt, B, (uint32_t)T, pref.data(), totals.data());
+        emu_launch_coop(k_aff_scan_tiles<G>, dim3(NB), (unsigned)PSCAN_THREADS, (const F*)totals.data(), (uint32_t)T, ps.data(), bp.data());
+        emu_launch_coop(k_aff_scan_top<G>, dim3(1), (unsigned)PSCAN_THREADS, (const F*)bp.data(), (uint32_t)NB, bp.data() + bp_stride,
+                        bp.data() + 2 * bp_stride);
+        if (l == 0)
+          LAUNCH(k_aff_backward<G, true>, dim3(nblk(T, 128)), 128u, points, (const uint32_t*)entries.data(), src_cur, off_cur, (const uint32_t*)off_next,
+                 nbt, B, (uint32_t)T, (const F*)pref.data(), (const F*)ps.data(), (const F*)(bp.data() + 2 * bp_stride), dst);
+        else
+          LAUNCH(k_aff_backward<G, false>, dim3(nblk(T, 128)), 128u, points, (const uint32_t*)entries.data(), src_cur, off_cur, (const uint32_t*)off_next,
+                 nbt, B, (uint32_t)T, (const F*)pref.data(), (const F*)ps.data(), (const F*)(bp.data() + 2 * bp_stride), dst);
+        src_cur = dst;
+        off_cur = off_next;
+        m_up = m_next;
+      }
+      if (nlevels == 0)
+        LAUNCH(k_aff_to_buckets<G, true>, dim3(std::min<unsigned>(nblk(nbt, 256), 8u)), 256u, points, (const uint32_t*)entries.data(), src_cur, off_cur, nbt,
+               buckets.data());
+      else
+        LAUNCH(k_aff_to_buckets<G, false>, dim3(std::min<unsigned>(nblk(nbt, 256), 8u)), 256u, points, (const uint32_t*)entries.data(), src_cur, off_cur, nbt,
+               buckets.data());
+      return 0;
+    }
     // K2: accumulate
     const uint32_t K = o.K;
     const size_t nchunks = (n * (size_t)p.nwin + K - 1) / K;
@@ -76,10 +157,10 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
     if (split > 0 && split < NPASS) {
       const uint32_t split_bucket = (uint32_t)std::min<uint64_t>((uint64_t)split * range_sz, p.nb_total);
       for (int part = 1; part <= 2; part++)
-        emu_launch(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
+        LAUNCH(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
                    p.nb_total, K, (uint32_t)nchunks, buckets.data(), carr0.data(), ids0.data(), part, split_bucket);
     } else {
-      emu_launch(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
+      LAUNCH(k_accumulate<G>, dim3(nblk(nchunks, 128)), 128, points, (const uint32_t*)entries.data(), (const uint32_t*)offsets.data(),
                  p.nb_total, K, (uint32_t)nchunks, buckets.data(), carr0.data(), ids0.data(), 0, 0u);
     }
     // K2b: carry levels
@@ -95,7 +176,7 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
         const uint32_t k2 = first ? o.K2_first : o.K2;
         first = false;
         const size_t n_out = (n_in + k2 - 1) / k2;
-        emu_launch(k_carry_level<G>, dim3(nblk(n_out, 128)), 128, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2, buckets.data(),
+        LAUNCH(k_carry_level<G>, dim3(nblk(n_out, 128)), 128, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2, buckets.data(),
                    cp[cur ^ 1], ip[cur ^ 1]);
         n_in = n_out;
         cur ^= 1;
@@ -123,7 +204,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     table.resize((size_t)p.nwin * std::max<size_t>(n, 1));
     if (n) std::memcpy(table.data(), points, n * sizeof(A));
     for (int j = 1; j < p.nwin && n; j++)
-      emu_launch(k_table_level<G>, dim3(nblk((n + TAB_M - 1) / TAB_M, 128)), 128, (const A*)(table.data() + (size_t)(j - 1) * n), n32, o.c,
+      LAUNCH(k_table_level<G>, dim3(nblk((n + TAB_M - 1) / TAB_M, 128)), 128, (const A*)(table.data() + (size_t)(j - 1) * n), n32, o.c,
                  table.data() + (size_t)j * n);
     points = table.data();
   }
@@ -140,7 +221,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     } else {
       std::vector<X> scratch_b(p.nb_total, X::inf());
       if (int rc = emu_accumulate<G>(points + lo, (uint32_t)n, scalars + lo, hi - lo, p, shared, o, scratch_b)) return rc;
-      emu_launch(k_merge_buckets<G>, dim3(nblk(p.nb_total, 128)), 128, buckets.data(), (const X*)scratch_b.data(), p.nb_total);
+      LAUNCH(k_merge_buckets<G>, dim3(nblk(p.nb_total, 128)), 128, buckets.data(), (const X*)scratch_b.data(), p.nb_total);
     }
   }
   // K3: bucket reduction
@@ -149,7 +230,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     const uint32_t L = o.L, S = (nbmax + L - 1) / L;
     const uint32_t nb_reg = shared ? p.nb_total : p.nb, nb_last = shared ? p.nb_total : p.nb_last;
     std::vector<X> seg0((size_t)red_windows * S), seg1((size_t)red_windows * ((S + 15) / 16) + 1);
-    emu_launch(k_bucket_segments<G>, dim3(nblk((size_t)red_windows * S, 128)), 128, (const X*)buckets.data(), red_windows, nb_reg, nb_last, L, S,
+    LAUNCH(k_bucket_segments<G>, dim3(nblk((size_t)red_windows * S, 128)), 128, (const X*)buckets.data(), red_windows, nb_reg, nb_last, L, S,
                seg0.data());
     uint32_t per = S;
     X* sp[2] = {seg0.data(), seg1.data()};
@@ -157,7 +238,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     while (per > 1) {
       const uint32_t R = 16, outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? partials.data() : sp[cur ^ 1];
-      emu_launch(k_sum_groups<G>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
+      LAUNCH(k_sum_groups<G>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
       per = outp;
       cur ^= 1;
     }
@@ -166,7 +247,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
   // K4: finalize
   std::vector<X> scratch(red_windows);
   Jac<F> out;
-  emu_launch(k_finalize<G>, dim3(1), 32, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  emu_launch_coop(k_finalize<G>, dim3(1), 32u, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }
@@ -192,9 +273,11 @@ using EmuG = bls12377_g2;
 #define EMU_CAT2(a, b) a##b
 #define EMU_CAT(a, b) EMU_CAT2(a, b)
 extern "C" int EMU_CAT(emu_msm_, EMU_GROUP)(const void* points, const void* scalars, size_t n, int c, int tables, uint32_t K, uint32_t K2_first,
-                                             uint32_t K2, uint32_t L, int passes, int split, int batches, void* out_jac) {
+                                             uint32_t K2, uint32_t L, int passes, int split, int batches, int mode, void* out_jac) {
   if (c < 2 || c > 24 || K < 1 || K2_first < 2 || K2 < 2 || L < 1) return 1;
-  Opts o{c, tables, K, K2_first, K2, L, passes, split, batches};
+  Opts o{c, tables, K, K2_first, K2, L, passes, split, batches, mode};
+  g_coop_all = (mode & 4) != 0;
+  if ((mode & 2) && (tables || batches > 1)) return 2;   // as in the engine: the batch-affine pass is plain, single-batch only
   return emu_msm<EmuG>(points, scalars, n, o, out_jac);
 }
 
@@ -203,7 +286,7 @@ extern "C" int EMU_CAT(emu_msm_, EMU_GROUP)(const void* points, const void* scal
 extern "C" int EMU_CAT(emu_generate_, EMU_GROUP)(const void* base, uint64_t start, size_t n, void* out) {
   using A = Affine<typename EmuG::F>;
   if (n == 0) return 0;
-  emu_launch(k_generate_multiples<EmuG>, dim3(nblk((n + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, start, (uint64_t)n, (A*)out);
+  LAUNCH(k_generate_multiples<EmuG>, dim3(nblk((n + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, start, (uint64_t)n, (A*)out);
   return 0;
 }
 extern "C" int EMU_CAT(emu_batch_scalar_mul_, EMU_GROUP)(const void* base, const void* scalars, size_t n, int c, void* out) {
@@ -212,8 +295,8 @@ extern "C" int EMU_CAT(emu_batch_scalar_mul_, EMU_GROUP)(const void* base, const
   const WindowPlan p = make_plan(EmuG::FrParams::BITS, c);
   const size_t tbl = (size_t)1 << (std::max(p.c, p.last_c) - 1);
   std::vector<A> table(tbl);
-  emu_launch(k_generate_multiples<EmuG>, dim3(nblk((tbl + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, (uint64_t)1, (uint64_t)tbl, table.data());
-  emu_launch(k_batch_scalar_mul<EmuG>, dim3(nblk(n, 128)), 128, (const A*)table.data(), (const typename EmuG::Fr*)scalars, (uint32_t)n, p.c, p.nwin,
+  LAUNCH(k_generate_multiples<EmuG>, dim3(nblk((tbl + GEN_M - 1) / GEN_M, 128)), 128, (const A*)base, (uint64_t)1, (uint64_t)tbl, table.data());
+  LAUNCH(k_batch_scalar_mul<EmuG>, dim3(nblk(n, 128)), 128, (const A*)table.data(), (const typename EmuG::Fr*)scalars, (uint32_t)n, p.c, p.nwin,
              (A*)out);
   return 0;
 }

@@ -4,8 +4,9 @@ compared with the oracle.  This checks the kernel-level logic without a GPU: dig
 and the shared (window-table) scatter, the chunked segmented reduction with its owner / carry rule and the two-part
 launch, the carry levels, the segment reduction, the finalize and the table level -- at chunk lengths, carry run
 lengths, segment lengths and pass counts the engine's own heuristics would not pick.  The device arithmetic itself
-(PTX carry chains) is covered by tests/test_hostcheck.py; the real launches by the -m gpu tests.  Threads run one after
-the other, so this finds logic errors, not data races (compute-sanitizer racecheck on the GPU does that:
+(PTX carry chains) is covered by tests/test_hostcheck.py; the real launches by the -m gpu tests.  Kernels with barriers or
+warp shuffles (the K1b scans, k_finalize, the product scans of the batch-affine pass) run under a cooperative launcher:
+one ucontext fiber per CUDA thread.  One thread runs at a time, so this finds logic errors, not data races (compute-sanitizer racecheck on the GPU does that:
 profiles/r01_compute_sanitizer_racecheck.log).  CPU only; a test artefact (build/libgmsm_emu.so), never part of libgmsm.so."""
 import ctypes
 import os
@@ -47,8 +48,11 @@ def _lib():
     return _LIB
 
 
-def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, split=0, batches=1, order=0):
-    """order: block execution order of every emulated launch (0 ascending, 1 descending, >= 2 pseudo-random)"""
+def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, split=0, batches=1, order=0, mode=0):
+    """order: block execution order of every emulated launch (0 ascending, 1 descending, >= 2 pseudo-random)
+    mode : bit 0 = the real K1b scan kernels (cooperative launch: fibers with barriers and warp shuffles) instead of a
+           host scan; bit 1 = batch-affine bucket accumulation (affine_kernels.cuh) instead of k_accumulate;
+           bit 2 = every launch through the cooperative launcher"""
     getattr(_lib(), "emu_set_block_order_%d" % GROUPS.index(g))(order)
     pts = np.ascontiguousarray(pts, dtype=np.uint64)
     s = np.ascontiguousarray(s, dtype=np.uint64)
@@ -56,7 +60,7 @@ def emu_msm(g, pts, s, c, tables=0, K=16, K2_first=4, K2=16, L=32, passes=4, spl
     out = np.zeros(3 * w, dtype=np.uint64)
     fn = getattr(_lib(), "emu_msm_%d" % GROUPS.index(g))
     rc = fn(pts.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(pts.shape[0]), c, tables,
-            K, K2_first, K2, L, passes, split, batches, out.ctypes.data_as(ctypes.c_void_p))
+            K, K2_first, K2, L, passes, split, batches, mode, out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0, rc
     return out
 
@@ -217,3 +221,45 @@ def test_emulated_kernels_block_order_independent(g, n):
     for order in (0, 1, 2, 5, 99):
         for tables in (0, 1):
             _check(g, emu_msm(g, pts, s, 6, tables=tables, K=4, passes=2, split=1, order=order), want)
+
+
+@pytest.mark.parametrize("tables", [0, 1])
+def test_emulated_real_scan_kernels(tables):
+    """K1b: k_scan_block_sums / k_scan_top / k_scan_final (block scans built on warp shuffles and barriers) under the
+    cooperative launcher, on histograms shorter and longer than one scan tile (2048 counters)"""
+    g = "bn254_g1"
+    pts, s = make_inputs(g, 700, 8)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c in (3, 9, 13):     # nb_total + 1 = 341 / 7169 (plain) counters ... up to 4097 shared
+        _check(g, emu_msm(g, pts, s, c, tables=tables, K=8, mode=1), want)
+    _check(g, emu_msm(g, pts, s, 7, tables=tables, K=8, split=2, mode=1 | 4), want)   # everything cooperative
+
+
+@pytest.mark.parametrize("g,n", [("bn254_g1", 900), ("bn254_g2", 200), ("bls12381_g1", 300)])
+def test_emulated_batch_affine_accumulation(g, n):
+    """the batch-affine bucket pass (GMSM_AFFINE=1; the GPU restatement of processChunkG1BatchAffine + batchAddG1Affine,
+    multiexp_affine.go:24-231, g1.go:1122-1182): tree levels over the bucket-ordered entries, forward / backward passes
+    around the hierarchical product scans with ONE inversion per level -- with duplicated points (doubling), P / -P
+    (cancellation), infinity points and zero scalars in the input"""
+    pts, s = make_inputs(g, n, 2718)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c, B, mode in ((4, 8, 2), (10, 3, 2 | 1), (13, 128, 2)):
+        _check(g, emu_msm(g, pts, s, c, K=B, mode=mode), want)
+
+
+@pytest.mark.parametrize("kind", ["one_bucket", "all_equal_points", "all_infinity", "single"])
+def test_emulated_batch_affine_skewed(kind):
+    g = "bn254_g1"
+    n = 600
+    pts, s = make_inputs(g, n, 56, specials=False)
+    if kind == "one_bucket":
+        s[:] = s[0]
+    elif kind == "all_equal_points":
+        pts[:] = pts[3]
+    elif kind == "all_infinity":
+        pts[:] = 0
+    else:
+        pts, s = pts[7:8], s[7:8]
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c in (5, 12):
+        _check(g, emu_msm(g, pts, s, c, K=8, mode=2 | 1), want)
