@@ -24,7 +24,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
-#define __shared__ static thread_local
+#define __shared__ thread_local   /* block scope: implies static; `extern __shared__ x[]` works too */
 
 struct uint4 {
   uint32_t x, y, z, w;
@@ -41,6 +41,11 @@ static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t atomicSub(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o - v; return o; }
 static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+static inline unsigned long long __brevll(unsigned long long v) {
+  unsigned long long r = 0;
+  for (int i = 0; i < 64; i++) r |= ((v >> i) & 1ull) << (63 - i);
+  return r;
+}
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
 }

@@ -42,6 +42,9 @@ def _lib():
                 # tests/emu FIRST: its cuda_runtime.h stands in for the real one
                 procs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-fPIC", "-DEMU_GROUP=%d" % k, "-I", EMU, "-I", CSRC, "-c",
                                                os.path.join(EMU, "emu_engine.cpp"), "-o", o]))
+            o = os.path.join(bdir, "emu_fft.o")
+            objs.append(o)
+            procs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-fPIC", "-I", EMU, "-I", CSRC, "-c", os.path.join(EMU, "emu_fft.cpp"), "-o", o]))
             assert all(p.wait() == 0 for p in procs)
             subprocess.run(["g++", "-shared", "-o", OUT, *objs], check=True)
         _LIB = ctypes.CDLL(OUT)
@@ -263,3 +266,57 @@ def test_emulated_batch_affine_skewed(kind):
     want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
     for c in (5, 12):
         _check(g, emu_msm(g, pts, s, c, K=8, mode=2 | 1), want)
+
+
+# ---- next-row N3: the Fr FFT kernels (fft_kernels.cuh) ----
+FR_FIELDS = ["bn254_fr", "bls12381_fr", "bls12377_fr"]
+
+
+def _emu_fft(frname, vals, inverse, decimation, coset, shift=None, bit_reverse_only=False):
+    f = O.FIELDS[frname]
+    n = len(vals)
+    logn = n.bit_length() - 1
+    od = O.FFTDomain(frname, n, shift=shift)
+    enc = lambda xs: np.array([f.to_limbs(f.to_mont(v)) for v in xs], dtype=np.uint64)
+    a = enc(vals)
+    consts = enc([od.generator, od.generator_inv, od.cardinality_inv, od.shift, od.shift_inv])
+    rc = _lib().emu_fft_run(FR_FIELDS.index(frname), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n), logn, int(inverse), int(decimation),
+                            int(coset), consts.ctypes.data_as(ctypes.c_void_p), int(bit_reverse_only))
+    assert rc == 0
+    return [f.from_mont(O.Field.from_limbs([int(x) for x in r])) for r in a], od
+
+
+@pytest.mark.parametrize("frname", FR_FIELDS)
+@pytest.mark.parametrize("logn", [0, 1, 3, 6, 10, 11, 12])
+def test_emulated_fft_kernels(frname, logn):
+    """Domain.FFT / FFTInverse (ecc/bn254/fr/fft/fft.go:31-190), both decimations, plain and on the coset: sizes below, at
+    and above the shared-memory tile (2^10), where the strided stages (k_fft_dif_stage / k_fft_dit_stage) join the tile
+    kernel (barriers: cooperative launcher)"""
+    import random
+
+    f = O.FIELDS[frname]
+    n = 1 << logn
+    rng = random.Random(100 + logn)
+    vals = [rng.randrange(f.q) for _ in range(n)]
+    cases = [(dec, coset) for dec in (O.DIT, O.DIF) for coset in (False, True)]
+    if logn >= 11 and frname != "bn254_fr":
+        cases = cases[1:3]                       # keep the big sizes cheap for the other fields
+    for dec, coset in cases:
+        got, od = _emu_fft(frname, vals, False, dec, coset)
+        assert got == od.fft(vals, dec, coset), (dec, coset)
+        got, od = _emu_fft(frname, vals, True, dec, coset)
+        assert got == od.fft_inverse(vals, dec, coset), (dec, coset)
+
+
+def test_emulated_fft_custom_shift_and_bit_reverse():
+    f = O.FIELDS["bn254_fr"]
+    n = 256
+    vals = [(7 * i * i + 3) % f.q for i in range(n)]
+    got, od = _emu_fft("bn254_fr", vals, False, O.DIF, True, shift=987654321)
+    assert got == od.fft(vals, O.DIF, True)
+    got, _ = _emu_fft("bn254_fr", vals, False, O.DIF, False, bit_reverse_only=True)      # fft.BitReverse (bitreverse.go:17-42)
+    assert got == O.bit_reverse(list(vals))
+    # DIF then DIT-inverse without any reordering is the identity (the composition gnark's provers use)
+    fwd, _ = _emu_fft("bn254_fr", vals, False, O.DIF, False)
+    back, _ = _emu_fft("bn254_fr", fwd, True, O.DIT, False)
+    assert back == vals
