@@ -357,10 +357,120 @@ GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
 }
 #endif
 
+// Dedicated Montgomery squaring (experimental: -DGMSM_SQR_DEDICATED=1, default off -- the reference's amd64 Square also
+// just calls mul(x, x), fp/element_amd64.go:51-55).  Same row-wise CIOS with the even / odd accumulator pair as
+// fp_mul_inline, but row i only multiplies x_i by the limbs j >= i of the operand: x_i itself on the diagonal and
+// twice the limbs above it (2 * (x >> 32(i+1)): the limbs of 2x, except that limb i+1 takes no bit from x_i) -- the
+// doubling cannot overflow the N limbs because the supported moduli leave at least two spare top bits -- so
+// N(N-1)/2 of the N^2 product IMAD.WIDEs disappear (28 of 64 for N = 8; the N^2 + N of the reduction stay: 108 instead of
+// 136 per squaring).  Skipped even columns still ripple the row's 1-bit carry-in (ADDC on the ALU pipe, which has
+// headroom: DESIGN.md section 5); skipped odd columns are plain moves of the frame shift.  The total added over the
+// rows is exactly x^2, so the result and its < 2q bound are unchanged; intermediate frames stay below 3q < 2^(32N).
+// The dropped-carry assertions (GMSM_NO_CARRY) are checked by the emulated host build like those of the multiplier.
+#if defined(GMSM_SQR_DEDICATED) && defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+template <class P>
+GMSM_HD Fp<P> fp_sqr_inline(const Fp<P>& x) {
+  constexpr int N = P::N;
+  static_assert((P::mod(N - 1) >> 30) == 0, "needs two spare top bits (2x in N limbs, frames below 3q)");
+  Fp<P> r;
+  uint32_t x2[N];   // limbs of 2x
+  x2[0] = x.l[0] << 1;
+#pragma unroll
+  for (int j = 1; j < N; j++) x2[j] = (x.l[j] << 1) | (x.l[j - 1] >> 31);
+  uint32_t A[N + 2], B[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
+  uint32_t dprev = 0, e0prev = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Ev = (i & 1) ? B : A;
+    uint32_t* Od = (i & 1) ? A : B;
+    const uint32_t bi = x.l[i];
+    const uint32_t d = (i == 0) ? 0u : Od[1];
+    // step 1: Ev += (operand limbs at even j >= i) * bi; columns below i only carry the row's carry-in upwards
+    if (i != 0) (void)add_cc(e0prev, dprev);
+    bool chain = (i != 0);   // is a carry chain running?  (compile-time after unrolling)
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      if (j < i) {
+        Ev[j] = addc_cc(Ev[j], 0);
+        Ev[j + 1] = addc_cc(Ev[j + 1], 0);
+      } else {
+        const uint32_t xj = (j == i) ? x.l[j] : (j == i + 1) ? (x.l[j] << 1) : x2[j];   // 2 * (the limbs above i): no bit from x_i
+        Ev[j] = chain ? madc_lo_cc(xj, bi, Ev[j]) : mad_lo_cc(xj, bi, Ev[j]);
+        Ev[j + 1] = madc_hi_cc(xj, bi, Ev[j + 1]);
+      }
+      chain = true;
+    }
+    Ev[N] = addc(0, 0);
+    // step 2: Od = (Od >> 2 limbs) + (operand limbs at odd j >= i) * bi   (no carry out; Od[N+1] == 0)
+    chain = false;
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      if (j + 1 < i) {
+        Od[j] = Od[j + 2];
+        Od[j + 1] = Od[j + 3];
+      } else {
+        const uint32_t xj = (j + 1 == i) ? x.l[j + 1] : (j == i) ? (x.l[j + 1] << 1) : x2[j + 1];
+        Od[j] = chain ? madc_lo_cc(xj, bi, Od[j + 2]) : mad_lo_cc(xj, bi, Od[j + 2]);
+        Od[j + 1] = madc_hi_cc(xj, bi, Od[j + 3]);
+        chain = true;
+      }
+    }
+    if (chain) GMSM_NO_CARRY();
+    Od[N] = 0;
+    // steps 3-5: the reduction of fp_mul_inline, unchanged
+    const uint32_t m = (Ev[0] + d) * P::INV;
+    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
+    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+    }
+    GMSM_NO_CARRY();
+    e0prev = Ev[0];
+    dprev = d;
+  }
+  (void)add_cc(e0prev, dprev);
+  r.l[0] = addc_cc(A[0], B[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(A[i], B[i + 1]);
+  r.l[N - 1] = addc(A[N - 1], B[N]);
+  fp_reduce_once(r);
+  return r;
+}
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp<P> fp_sqr_ni(Fp<P> x) {
+  return fp_sqr_inline(x);
+}
+template <class P>
+GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {
+  if constexpr ((P::mod(P::N - 1) >> 30) == 0) return fp_sqr_ni<P>(x);
+  else return fp_mul(x, x);   // one spare bit only (bls12-381 fr): keep the multiplier
+}
+#else
+template <class P>
+GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {
+  if constexpr ((P::mod(P::N - 1) >> 30) == 0) return fp_sqr_inline(x);
+  else return fp_mul(x, x);
+}
+#endif
+#else
 template <class P>
 GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {
   return fp_mul(x, x);
 }
+#endif
 
 // Montgomery -> canonical: multiply by 1 (fromMont, fr/element.go:593-642)
 template <class P>

@@ -21,13 +21,14 @@ _LIBS = {}
 def _build(variant):
     """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
     if variant not in _LIBS:
-        tag = "" if variant == "portable" else "_emu"
+        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr"}[variant]
         out = OUT % tag
         bdir = os.path.dirname(out)
         os.makedirs(bdir, exist_ok=True)
         srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h", ".cpp"))]
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in srcs):
-            flags = ["-std=c++17", "-O1", "-fPIC"] + ([] if variant == "portable" else ["-DGMSM_EMULATE_PTX"])
+            flags = ["-std=c++17", "-O1", "-fPIC"] + {"portable": [], "emulated": ["-DGMSM_EMULATE_PTX"],
+                                                     "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
             for k in list(range(6)) + [None]:
@@ -40,7 +41,8 @@ def _build(variant):
     return _LIBS[variant]
 
 
-@pytest.fixture(scope="module", params=["portable", "emulated"])
+# "emulated_sqr": the experimental dedicated squaring of field.cuh (-DGMSM_SQR_DEDICATED=1, not in the default build)
+@pytest.fixture(scope="module", params=["portable", "emulated", "emulated_sqr"])
 def hc(request):
     return _build(request.param)
 
@@ -133,6 +135,9 @@ def test_carry_chain_mul_sqr_stress(g):
     mp, me = run_p(0, A, B, nl), run_e(0, A, B, nl)
     sp, se = run_p(3, A, None, nl), run_e(3, A, None, nl)
     assert np.array_equal(mp, me) and np.array_equal(sp, se)
+    # the experimental dedicated squaring (rows restricted to the limbs j >= i, doubled operand above the diagonal)
+    sq = _runner(_build("emulated_sqr"), g)(3, A, None, nl)
+    assert np.array_equal(sq, sp)
     got_m = [f.from_limbs(row) for row in me.view(np.uint64)]
     got_s = [f.from_limbs(row) for row in se.view(np.uint64)]
     assert got_m == [vals[i] * vals[perm[i]] * f.Rinv % f.q for i in range(len(vals))]
