@@ -51,10 +51,16 @@ GMSM_HD XYZZ<F> xyzz_double_affine(const F& x, const F& y) {
   F XX = f_sqr(x);
   F M = f_add(f_dbl(XX), XX);
   F S2 = f_dbl(S);
+#if defined(GMSM_DOT2)
+  XYZZ<F> r;
+  r.x = f_sub(f_sqr(M), S2);
+  r.y = f_dot2(f_sub(S, r.x), M, W, f_neg(y));   // (S - X3) M - W y with one reduction (experimental, field.cuh)
+#else
   F L = f_mul(W, y);
   XYZZ<F> r;
   r.x = f_sub(f_sqr(M), S2);
   r.y = f_sub(f_mul(f_sub(S, r.x), M), L);
+#endif
   r.zz = V;
   r.zzz = W;
   return r;
@@ -88,7 +94,11 @@ GMSM_HD void xyzz_add_mixed(XYZZ<F>& p, const Affine<F>& a, bool negate) {
   F Q = f_mul(p.x, PP);
   F RR = f_sqr(R);
   F X3 = f_sub(f_sub(RR, PPP), f_dbl(Q));
+#if defined(GMSM_DOT2)
+  F Y3 = f_dot2(f_sub(Q, X3), R, f_neg(p.y), PPP);   // (Q - X3) R - Y1 PPP with one reduction (experimental, field.cuh)
+#else
   F Y3 = f_sub(f_mul(f_sub(Q, X3), R), f_mul(p.y, PPP));
+#endif
   p.x = X3;
   p.y = Y3;
   p.zz = f_mul(p.zz, PP);
@@ -139,9 +149,14 @@ GMSM_HD void xyzz_add(XYZZ<F>& p, const XYZZ<F>& q) {
   F PP = f_sqr(P);
   F PPP = f_mul(P, PP);
   F Q = f_mul(U1, PP);
+#if defined(GMSM_DOT2)
+  F X3 = f_sub(f_sub(f_sub(f_sqr(R), PPP), Q), Q);
+  F Y3 = f_dot2(f_sub(Q, X3), R, f_neg(S1), PPP);
+#else
   F V = f_mul(S1, PPP);
   F X3 = f_sub(f_sub(f_sub(f_sqr(R), PPP), Q), Q);
   F Y3 = f_sub(f_mul(f_sub(Q, X3), R), V);
+#endif
   p.x = X3;
   p.y = Y3;
   p.zz = f_mul(f_mul(p.zz, q.zz), PP);

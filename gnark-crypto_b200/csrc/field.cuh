@@ -472,6 +472,121 @@ GMSM_HD Fp<P> fp_sqr(const Fp<P>& x) {
 }
 #endif
 
+// Sum of two products with ONE reduction (experimental: -DGMSM_DOT2=1, default off):  z = (x*y + u*v) * R^-1 mod q.
+// The rows of the CIOS take both products (two MAD chains per accumulator and row) and share the reduction steps:
+// 2 N^2 product + N^2 + N reduction IMAD.WIDEs = 200 for N = 8 instead of 272 for two multiplications, and one
+// conditional subtraction instead of two plus the fp_sub -- no extra ALU work at all.  Used for the y-coordinate of the
+// point additions (Y3 = (Q - X3) * R + (-Y1) * PPP, curve.cuh), 5 % of a mixed addition's multiplier work.  Needs the
+// two spare top bits like the dedicated squaring: frames stay below 3q < 2^(32N), the result below (2q/2^(32N) + 1) q < 2q.
+#if defined(GMSM_DOT2) && defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+template <class P>
+GMSM_HD Fp<P> fp_dot2_inline(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P>& v) {
+  constexpr int N = P::N;
+  static_assert((P::mod(N - 1) >> 30) == 0, "needs two spare top bits (frames below 3q)");
+  Fp<P> r;
+  uint32_t A[N + 2], B[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
+  uint32_t dprev = 0, e0prev = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Ev = (i & 1) ? B : A;
+    uint32_t* Od = (i & 1) ? A : B;
+    const uint32_t bi = y.l[i], vi = v.l[i];
+    const uint32_t d = (i == 0) ? 0u : Od[1];
+    // step 1a: Ev += x_even * bi (with the row's carry-in), 1b: Ev += u_even * vi
+    if (i == 0) {
+      Ev[0] = mad_lo_cc(x.l[0], bi, Ev[0]);
+    } else {
+      (void)add_cc(e0prev, dprev);
+      Ev[0] = madc_lo_cc(x.l[0], bi, Ev[0]);
+    }
+    Ev[1] = madc_hi_cc(x.l[0], bi, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(x.l[j], bi, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(x.l[j], bi, Ev[j + 1]);
+    }
+    Ev[N] = addc(0, 0);
+    Ev[0] = mad_lo_cc(u.l[0], vi, Ev[0]);
+    Ev[1] = madc_hi_cc(u.l[0], vi, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(u.l[j], vi, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(u.l[j], vi, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    // step 2a: Od = (Od >> 2 limbs) + x_odd * bi, 2b: Od += u_odd * vi   (no carry out of either)
+    Od[0] = mad_lo_cc(x.l[1], bi, Od[2]);
+    Od[1] = madc_hi_cc(x.l[1], bi, Od[3]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(x.l[j + 1], bi, Od[j + 2]);
+      Od[j + 1] = madc_hi_cc(x.l[j + 1], bi, Od[j + 3]);
+    }
+    GMSM_NO_CARRY();
+    Od[N] = 0;
+    Od[0] = mad_lo_cc(u.l[1], vi, Od[0]);
+    Od[1] = madc_hi_cc(u.l[1], vi, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(u.l[j + 1], vi, Od[j]);
+      Od[j + 1] = madc_hi_cc(u.l[j + 1], vi, Od[j + 1]);
+    }
+    GMSM_NO_CARRY();
+    // steps 3-5: the reduction of fp_mul_inline, unchanged
+    const uint32_t m = (Ev[0] + d) * P::INV;
+    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
+    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+    }
+    GMSM_NO_CARRY();
+    e0prev = Ev[0];
+    dprev = d;
+  }
+  (void)add_cc(e0prev, dprev);
+  r.l[0] = addc_cc(A[0], B[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(A[i], B[i + 1]);
+  r.l[N - 1] = addc(A[N - 1], B[N]);
+  fp_reduce_once(r);
+  return r;
+}
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp<P> fp_dot2_ni(Fp<P> x, Fp<P> y, Fp<P> u, Fp<P> v) {
+  return fp_dot2_inline(x, y, u, v);
+}
+#endif
+#endif
+// x*y + u*v: the fused form above where it is compiled in and the modulus has the spare bits, two products otherwise
+template <class P>
+GMSM_HD Fp<P> fp_dot2(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P>& v) {
+#if defined(GMSM_DOT2) && defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+  if constexpr ((P::mod(P::N - 1) >> 30) == 0) {
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+    return fp_dot2_ni<P>(x, y, u, v);
+#else
+    return fp_dot2_inline(x, y, u, v);
+#endif
+  } else
+#endif
+  {
+    return fp_add(fp_mul(x, y), fp_mul(u, v));
+  }
+}
+
 // Montgomery -> canonical: multiply by 1 (fromMont, fr/element.go:593-642)
 template <class P>
 GMSM_HD Fp<P> fp_from_mont(const Fp<P>& x) {
@@ -522,6 +637,7 @@ template <class P> GMSM_HD Fp<P> f_add(const Fp<P>& a, const Fp<P>& b) { return 
 template <class P> GMSM_HD Fp<P> f_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
 template <class P> GMSM_HD Fp<P> f_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
 template <class P> GMSM_HD Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
+template <class P> GMSM_HD Fp<P> f_dot2(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P>& v) { return fp_dot2(x, y, u, v); }
 template <class P> GMSM_HD Fp<P> f_dbl(const Fp<P>& a) { return fp_dbl(a); }
 template <class P> GMSM_HD Fp<P> f_neg(const Fp<P>& a) { return fp_neg(a); }
 template <class P> GMSM_HD Fp<P> f_inv(const Fp<P>& a) { return fp_inv(a); }

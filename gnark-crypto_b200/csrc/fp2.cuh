@@ -58,6 +58,12 @@ GMSM_HD Fp2<P> f_sqr(const Fp2<P>& x) {
   return Fp2<P>{a, b};
 }
 
+// x*y + u*v over Fp2: no fused form (Karatsuba already shares the work), plain composition
+template <class P>
+GMSM_HD Fp2<P> f_dot2(const Fp2<P>& x, const Fp2<P>& y, const Fp2<P>& u, const Fp2<P>& v) {
+  return f_add(f_mul(x, y), f_mul(u, v));
+}
+
 // (a0 - a1 u) / (a0^2 + a1^2)   (e2_bn254.go:61-73)
 template <class P>
 GMSM_HD Fp2<P> f_inv(const Fp2<P>& x) {

@@ -38,6 +38,13 @@ using HcG = bls12377_g2;
 extern "C" int HC_CAT(hostcheck_op_, HC_GROUP)(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   return run<HcG>(op, a, b, o, n);
 }
+// out = (x*y + u*v) in the coordinate field (f_dot2: the fused two-product routine when built with -DGMSM_DOT2=1)
+extern "C" int HC_CAT(hostcheck_dot2_, HC_GROUP)(const uint32_t* x, const uint32_t* y, const uint32_t* u, const uint32_t* v, uint32_t* o, size_t n) {
+  using F = typename HcG::F;
+  constexpr int W = sizeof(F) / 4;
+  for (size_t i = 0; i < n; i++) wr(o + i * W, f_dot2(rd<F>(x + i * W), rd<F>(y + i * W), rd<F>(u + i * W), rd<F>(v + i * W)));
+  return 0;
+}
 // one window-table level on the CPU, batched exactly like k_table_level: out[i] = 2^c * in[i] (affine, u32 words)
 extern "C" int HC_CAT(hostcheck_table_level_, HC_GROUP)(int c, const uint32_t* in, size_t n, uint32_t* out) {
   using F = typename HcG::F;
@@ -66,6 +73,19 @@ int hostcheck_table_level_2(int, const uint32_t*, size_t, uint32_t*);
 int hostcheck_table_level_3(int, const uint32_t*, size_t, uint32_t*);
 int hostcheck_table_level_4(int, const uint32_t*, size_t, uint32_t*);
 int hostcheck_table_level_5(int, const uint32_t*, size_t, uint32_t*);
+}
+extern "C" {
+int hostcheck_dot2_0(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_dot2_2(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+int hostcheck_dot2_4(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+}
+extern "C" int hostcheck_dot2(int curve, const uint32_t* x, const uint32_t* y, const uint32_t* u, const uint32_t* v, uint32_t* o, size_t n) {
+  switch (curve) {   // the G1 groups: coordinate field = Fp
+    case 0: return hostcheck_dot2_0(x, y, u, v, o, n);
+    case 2: return hostcheck_dot2_2(x, y, u, v, o, n);
+    case 4: return hostcheck_dot2_4(x, y, u, v, o, n);
+  }
+  return 1;
 }
 extern "C" int hostcheck_table_level(int curve, int c, const uint32_t* in, size_t n, uint32_t* out) {
   switch (curve) {

@@ -28,7 +28,7 @@ def _build(variant):
         srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h", ".cpp"))]
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in srcs):
             flags = ["-std=c++17", "-O1", "-fPIC"] + {"portable": [], "emulated": ["-DGMSM_EMULATE_PTX"],
-                                                     "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1"]}[variant]
+                                                     "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
             for k in list(range(6)) + [None]:
@@ -41,7 +41,8 @@ def _build(variant):
     return _LIBS[variant]
 
 
-# "emulated_sqr": the experimental dedicated squaring of field.cuh (-DGMSM_SQR_DEDICATED=1, not in the default build)
+# "emulated_sqr": the experimental dedicated squaring and fused two-product routine of field.cuh
+# (-DGMSM_SQR_DEDICATED=1 -DGMSM_DOT2=1, not in the default build); the point formulas of curve.cuh then use them
 @pytest.fixture(scope="module", params=["portable", "emulated", "emulated_sqr"])
 def hc(request):
     return _build(request.param)
@@ -138,6 +139,21 @@ def test_carry_chain_mul_sqr_stress(g):
     # the experimental dedicated squaring (rows restricted to the limbs j >= i, doubled operand above the diagonal)
     sq = _runner(_build("emulated_sqr"), g)(3, A, None, nl)
     assert np.array_equal(sq, sp)
+    # the experimental fused two-product routine: (x*y + u*v) R^-1 with one reduction, against big-int arithmetic and
+    # against its plain composition (two products and an addition) in the portable build
+    C, D = A[rng.permutation(len(vals))], A[rng.permutation(len(vals))]
+    cid = list(O.GROUPS).index(g)
+    outs = []
+    for variant in ("portable", "emulated_sqr"):
+        out = np.zeros_like(A)
+        vp = ctypes.c_void_p
+        assert _build(variant).hostcheck_dot2(cid, A.ctypes.data_as(vp), B.ctypes.data_as(vp), C.ctypes.data_as(vp), D.ctypes.data_as(vp),
+                                              out.ctypes.data_as(vp), ctypes.c_size_t(len(vals))) == 0
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    lim = lambda M: [f.from_limbs(row) for row in np.ascontiguousarray(M).view(np.uint64)]
+    a_, b_, c_, d_ = lim(A), lim(B), lim(C), lim(D)
+    assert lim(outs[1]) == [(x * y + u * v) * f.Rinv % f.q for x, y, u, v in zip(a_, b_, c_, d_)]
     got_m = [f.from_limbs(row) for row in me.view(np.uint64)]
     got_s = [f.from_limbs(row) for row in se.view(np.uint64)]
     assert got_m == [vals[i] * vals[perm[i]] * f.Rinv % f.q for i in range(len(vals))]

@@ -19,7 +19,7 @@ def count(obj, kern):
             print("%-28s total=%6d IMAD.WIDE=%5d IMAD(other)=%5d IADD3=%5d SHF=%4d LOP3=%4d ISETP=%4d CALL=%3d" % (
                 k[:28], c["TOTAL"], wide, sum(v for kk, v in c.items() if kk.startswith("IMAD") and not kk.startswith("IMAD.WIDE")),
                 c["IADD3"], c["SHF"], c["LOP3"], c["ISETP"], c["CALL"]))
-for tag in ("build", "build_sqr"):
+for tag in sys.argv[1:] or ("build",):
     print("==", tag)
     count("%s/inst_bn254_g1.o" % tag, "k_accumulate")
     count("%s/inst_bls12381_g1.o" % tag, "k_accumulate")
