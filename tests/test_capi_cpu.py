@@ -70,3 +70,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle/|libmsmref", src, re.M), f
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/gmsm.h is what a cgo shim compiles: it must be valid C (no C++-isms) and a C program must
+    link against libgmsm.so and get the reference layout sizes"""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text('#include "gmsm.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %s\\n", gmsm_affine_bytes(GMSM_BN254_G1), gmsm_affine_bytes(GMSM_BLS12381_G2),\n'
+                   '  gmsm_jac_bytes(GMSM_BN254_G2), gmsm_scalar_bytes(GMSM_BLS12377_G1), gmsm_version()); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "gnark-crypto_b200")
+    cuda = "/usr/local/cuda/lib64"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lgmsm", "-L", cuda, "-lcudart", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[:4] == ["64", "192", "192", "32"] and out[4].startswith("gmsm-b200")
