@@ -26,6 +26,7 @@ struct Opts {
   int passes;         // bucket-range passes of the shared scatter
   int split;          // > 0: two-part accumulate, split after `split` windows / passes
   int batches;        // > 1: pipelined batches (scratch buckets + k_merge_buckets)
+  void* partials_out; // non-null: write the W (or 1) window partials there and skip the finalize
   int mode;           // bit 0: the real K1b scan kernels (block scans with warp shuffles) instead of a host scan
                       // bit 1: batch-affine bucket accumulation (affine_kernels.cuh, GMSM_AFFINE=1) instead of k_accumulate
                       // bit 2: every launch through the cooperative (fiber) launcher
@@ -244,10 +245,28 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     }
     if (S == 1) std::memcpy(partials.data(), seg0.data(), (size_t)red_windows * sizeof(X));
   }
+  if (o.partials_out) {   // one rank of a sharded MSM: stop after the bucket reduction (gmsm_ctx_window_sums_device)
+    std::memcpy(o.partials_out, partials.data(), (size_t)red_windows * sizeof(X));
+    return 0;
+  }
   // K4: finalize
   std::vector<X> scratch(red_windows);
   Jac<F> out;
   emu_launch_coop(k_finalize<G>, dim3(1), 32u, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  std::memcpy(out_jac, &out, sizeof(out));
+  return 0;
+}
+
+// gmsm_ctx_finalize_device: nranks x W gathered partials (rank-major) -> per-window sum over the ranks, Horner, normal form
+template <class G>
+int emu_finalize(const void* partials, int nranks, int c, int tables, void* out_jac) {
+  using F = typename G::F;
+  using X = XYZZ<F>;
+  const WindowPlan p = make_plan(G::FrParams::BITS, c);
+  const int red_windows = tables ? 1 : p.nwin;
+  std::vector<X> scratch(red_windows);
+  Jac<F> out;
+  emu_launch_coop(k_finalize<G>, dim3(1), 32u, (const X*)partials, nranks, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }
@@ -275,7 +294,7 @@ using EmuG = bls12377_g2;
 extern "C" int EMU_CAT(emu_msm_, EMU_GROUP)(const void* points, const void* scalars, size_t n, int c, int tables, uint32_t K, uint32_t K2_first,
                                              uint32_t K2, uint32_t L, int passes, int split, int batches, int mode, void* out_jac) {
   if (c < 2 || c > 24 || K < 1 || K2_first < 2 || K2 < 2 || L < 1) return 1;
-  Opts o{c, tables, K, K2_first, K2, L, passes, split, batches, mode};
+  Opts o{c, tables, K, K2_first, K2, L, passes, split, batches, nullptr, mode};
   g_coop_all = (mode & 4) != 0;
   if ((mode & 2) && (tables || batches > 1)) return 2;   // as in the engine: the batch-affine pass is plain, single-batch only
   return emu_msm<EmuG>(points, scalars, n, o, out_jac);
@@ -302,3 +321,13 @@ extern "C" int EMU_CAT(emu_batch_scalar_mul_, EMU_GROUP)(const void* base, const
 }
 
 extern "C" void EMU_CAT(emu_set_block_order_, EMU_GROUP)(unsigned order) { emu_block_order = order; }
+
+// one rank's window partials (W x xyzz, or 1 in window-table mode), and the combine over ranks
+extern "C" int EMU_CAT(emu_window_sums_, EMU_GROUP)(const void* points, const void* scalars, size_t n, int c, int tables, uint32_t K, void* out_partials) {
+  Opts o{c, tables, K, 4, 16, 32, 3, 1, 1, out_partials, 0};
+  g_coop_all = false;
+  return emu_msm<EmuG>(points, scalars, n, o, nullptr);
+}
+extern "C" int EMU_CAT(emu_finalize_, EMU_GROUP)(const void* partials, int nranks, int c, int tables, void* out_jac) {
+  return emu_finalize<EmuG>(partials, nranks, c, tables, out_jac);
+}

@@ -320,3 +320,31 @@ def test_emulated_fft_custom_shift_and_bit_reverse():
     fwd, _ = _emu_fft("bn254_fr", vals, False, O.DIF, False)
     back, _ = _emu_fft("bn254_fr", fwd, True, O.DIT, False)
     assert back == vals
+
+
+@pytest.mark.parametrize("g,tables", [("bn254_g1", 0), ("bn254_g1", 1), ("bn254_g2", 0)])
+def test_emulated_sharded_window_sums_and_finalize(g, tables):
+    """the multi-GPU decomposition (gnark-crypto_b200/dist.py): contiguous shards, W window partials per rank
+    (one in window-table mode), gathered rank-major, k_finalize sums them per window over the ranks before the Horner --
+    the reference's analogue is the recursive split joined by AddAssign (multiexp.go:128-140)"""
+    n = 600 if g == "bn254_g1" else 150
+    pts, s = make_inputs(g, n, 4)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    lib = _lib()
+    k = GROUPS.index(g)
+    w = pts.shape[1] // 2
+    vp = ctypes.c_void_p
+    for c in (6, 11):
+        W = 1 if tables else O.compute_nb_chunks(O.GROUPS[g].fr.bits, c)
+        cuts = [0, n // 7, n // 2, n - 1, n]              # four ranks, one of them with a single point
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = np.zeros(W * 4 * w, dtype=np.uint64)
+            P, S = np.ascontiguousarray(pts[a:b]), np.ascontiguousarray(s[a:b])
+            assert getattr(lib, "emu_window_sums_%d" % k)(P.ctypes.data_as(vp), S.ctypes.data_as(vp), ctypes.c_size_t(b - a), c, tables, 8,
+                                                          part.ctypes.data_as(vp)) == 0
+            parts.append(part)
+        gathered = np.concatenate(parts)
+        out = np.zeros(3 * w, dtype=np.uint64)
+        assert getattr(lib, "emu_finalize_%d" % k)(gathered.ctypes.data_as(vp), len(parts), c, tables, out.ctypes.data_as(vp)) == 0
+        _check(g, out, want)
