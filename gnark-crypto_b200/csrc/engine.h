@@ -49,12 +49,18 @@ struct gmsm_ctx {
   uint32_t K2_first = 4;    // items per thread of the first carry level (GMSM_K2_FIRST): 4x the threads for the level that
                             // holds nearly all the carry additions (measured 0.87 -> 0.73 ms at bn254 G1 2^24)
   uint32_t seg_L = 32, seg_S = 0;
+  // lane-parallel tail (quad.cuh): a stage with `items` independent chains runs one QUAD of lanes per chain when four
+  // times the threads still fit the machine in about one wave (latency-bound regime); GMSM_QUAD=0 / 1 forces it off / on
+  int quad_mode = -1;
+  size_t quad_max_items = 148 * 512;
+  bool use_quad(size_t items) const { return quad_mode < 0 ? items <= quad_max_items : quad_mode != 0; }
   // device workspace
   uint32_t* hist = nullptr;      // nb_total + 1 (+pad)
   uint32_t* offsets = nullptr;   // nb_total + 1
   uint32_t* block_sums = nullptr;
   uint32_t* entries = nullptr;   // max_n * W (+pad)
   uint32_t* digits = nullptr;    // max_n * W, chunk-major (digits[j*n + i])
+  uint32_t* ranks = nullptr;     // max_n * W, same layout: position of the entry inside its bucket (numbered by K1's atomics)
   void* buckets = nullptr;       // nb_total xyzz
   void* buckets2 = nullptr;      // scratch buckets of a follow-up batch (pipelined calls), allocated on demand
   void* carries[2] = {nullptr, nullptr};
@@ -83,6 +89,9 @@ struct gmsm_ctx {
   int split_tab = 1;                   // the same for the bucket-range passes of the window-table mode
   cudaStream_t aux = nullptr;          // auxiliary stream: scatter of the later windows under the accumulate
   cudaEvent_t ev_split[2] = {};
+  // completion of the last call enqueued on this context: every device-level entry point makes its stream wait for it
+  // before touching the shared workspace, so calls from different streams / threads queue up instead of overlapping
+  cudaEvent_t ev_done = nullptr;
   float stage_ms[8] = {};
   bool have_stage = false;
   std::mutex mu;

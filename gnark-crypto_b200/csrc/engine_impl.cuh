@@ -38,7 +38,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->hist);
+    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->ranks, c->hist);
     launches++;
     LAUNCH_CHECK();
   }
@@ -78,7 +78,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
       const uint32_t blo = std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
       const uint32_t bhi = std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
       if (blo >= bhi) return;
-      k_scatter_shared<<<dim3(blocks, (unsigned)p.nwin), 256, 0, s>>>(c->digits, n32, c->tab_stride, c->hist, c->offsets,
+      k_scatter_shared<<<dim3(blocks, (unsigned)p.nwin), 256, 0, s>>>(c->digits, c->ranks, n32, c->tab_stride, c->offsets,
                                                                        c->entries, blo, bhi);
       launches++;
     };
@@ -93,7 +93,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   } else {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 8u);
     auto scatter = [&](int j, cudaStream_t s) {
-      k_scatter_window<<<blocks, 256, 0, s>>>(c->digits + (size_t)j * n, n32, c->hist + (size_t)j * p.nb,
+      k_scatter_window<<<blocks, 256, 0, s>>>(c->digits + (size_t)j * n, c->ranks + (size_t)j * n, n32,
                                               c->offsets + (size_t)j * p.nb, c->entries);
       launches++;
     };
@@ -203,9 +203,14 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
         // means more threads for the same work; the later levels see mostly empty slots
         const uint32_t k2 = (cur == 0 && n_in == nchunks) ? c->K2_first : c->K2;
         size_t n_out = (n_in + k2 - 1) / k2;
-        k_carry_level<G><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
-                                                          (uint32_t)n_in, k2, buckets,
-                                                          reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
+        if (c->use_quad(n_out))
+          k_carry_level<G, true><<<nblk(n_out * 4, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
+                                                                    (uint32_t)n_in, k2, buckets,
+                                                                    reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
+        else
+          k_carry_level<G, false><<<nblk(n_out, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->carries[cur]), c->carry_ids[cur],
+                                                                   (uint32_t)n_in, k2, buckets,
+                                                                   reinterpret_cast<X*>(c->carries[cur ^ 1]), c->carry_ids[cur ^ 1]);
         launches++;
         LAUNCH_CHECK();
         n_in = n_out;
@@ -238,8 +243,12 @@ static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
     // window-table mode: one window of nb_total shared buckets
     const int nwin = c->red_windows();
     const uint32_t nb_reg = c->shared ? p.nb_total : p.nb, nb_last = c->shared ? p.nb_total : p.nb_last;
-    k_bucket_segments<G><<<nblk((size_t)nwin * S, 128), 128, 0, st>>>(buckets, nwin, nb_reg, nb_last, L, S,
-                                                                     reinterpret_cast<X*>(c->seg[0]));
+    if (c->use_quad((size_t)nwin * S))
+      k_bucket_segments<G, true><<<nblk((size_t)nwin * S * 4, 128), 128, 0, st>>>(buckets, nwin, nb_reg, nb_last, L, S,
+                                                                             reinterpret_cast<X*>(c->seg[0]));
+    else
+      k_bucket_segments<G, false><<<nblk((size_t)nwin * S, 128), 128, 0, st>>>(buckets, nwin, nb_reg, nb_last, L, S,
+                                                                          reinterpret_cast<X*>(c->seg[0]));
     launches++;
     LAUNCH_CHECK();
     uint32_t per = S;
@@ -248,8 +257,12 @@ static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
       uint32_t R = 16;
       uint32_t outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? reinterpret_cast<X*>(d_partials) : reinterpret_cast<X*>(c->seg[cur ^ 1]);
-      k_sum_groups<G><<<nblk((size_t)nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
-                                                                     nwin, dst);
+      if (c->use_quad((size_t)nwin * outp))
+        k_sum_groups<G, true><<<nblk((size_t)nwin * outp * 4, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
+                                                                             nwin, dst);
+      else
+        k_sum_groups<G, false><<<nblk((size_t)nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
+                                                                          nwin, dst);
       launches++;
       LAUNCH_CHECK();
       per = outp;
@@ -275,7 +288,7 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
 template <class G>
 static int run_finalize(gmsm_ctx* c, const void* d_partials, int nranks, void* d_out, cudaStream_t st) {
   using F = typename G::F;
-  k_finalize<G><<<1, 32, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
+  k_finalize<G><<<1, FIN_THREADS, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
                                   reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
   LAUNCH_CHECK();
   return GMSM_OK;

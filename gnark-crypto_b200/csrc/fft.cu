@@ -176,27 +176,32 @@ extern "C" int gmsm_fft_domain_constants(const gmsm_fft_domain_t* d, uint64_t ou
   return GMSM_OK;
 }
 
+// unlocked dispatcher: callers hold d->mu
+static int fft_dispatch(gmsm_fft_domain_t* d, void* d_a, int inverse, int decimation, int coset, cudaStream_t st) {
+  CK(cudaSetDevice(d->device));
+  if (d->field == 0) return run_fft<bn254_fr>(d, d_a, inverse, decimation, coset, st);
+  if (d->field == 1) return run_fft<bls12381_fr>(d, d_a, inverse, decimation, coset, st);
+  return run_fft<bls12377_fr>(d, d_a, inverse, decimation, coset, st);
+}
+
 extern "C" int gmsm_fft_device(gmsm_fft_domain_t* d, void* d_a, size_t n, int inverse, int decimation, int coset, void* stream) {
   if (!d) return set_err(GMSM_EINVAL, "null domain");
   if (n != d->n) return set_err(GMSM_EINVAL, "len(a) = %zu must equal the domain cardinality %llu", n, (unsigned long long)d->n);
   if (decimation != 0 && decimation != 1) return set_err(GMSM_EINVAL, "not implemented");  // fft.go:108
   std::lock_guard<std::mutex> lk(d->mu);
-  CK(cudaSetDevice(d->device));
-  if (d->field == 0) return run_fft<bn254_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
-  if (d->field == 1) return run_fft<bls12381_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
-  return run_fft<bls12377_fr>(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
+  return fft_dispatch(d, d_a, inverse, decimation, coset, (cudaStream_t)stream);
 }
 
+// host vector in, host vector out: the domain's staging buffer d_buf is shared by all callers, so the domain mutex is held
+// across the whole H2D -> transform -> D2H sequence (two concurrent calls used to interleave on the buffer)
 static int fft_host(gmsm_fft_domain_t* d, uint64_t* a, size_t n, int inverse, int decimation, int coset) {
   if (!d) return set_err(GMSM_EINVAL, "null domain");
   if (n != d->n) return set_err(GMSM_EINVAL, "len(a) = %zu must equal the domain cardinality %llu", n, (unsigned long long)d->n);
-  {
-    std::lock_guard<std::mutex> lk(d->mu);
-    CK(cudaSetDevice(d->device));
-    CK(cudaMemcpy(d->d_buf, a, n * 32, cudaMemcpyHostToDevice));
-  }
-  if (int rc = gmsm_fft_device(d, d->d_buf, n, inverse, decimation, coset, nullptr)) return rc;
+  if (decimation != 0 && decimation != 1) return set_err(GMSM_EINVAL, "not implemented");  // fft.go:108
   std::lock_guard<std::mutex> lk(d->mu);
+  CK(cudaSetDevice(d->device));
+  CK(cudaMemcpy(d->d_buf, a, n * 32, cudaMemcpyHostToDevice));
+  if (int rc = fft_dispatch(d, d->d_buf, inverse, decimation, coset, nullptr)) return rc;
   CK(cudaMemcpy(a, d->d_buf, n * 32, cudaMemcpyDeviceToHost));
   return GMSM_OK;
 }

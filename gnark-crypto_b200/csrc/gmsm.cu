@@ -4,11 +4,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -133,6 +136,7 @@ static int ctx_alloc(gmsm_ctx* c) {
   const size_t ent = c->max_n * (size_t)p.nwin;
   CK(dmalloc(&c->entries, (ent + 16) * 4, &acc));
   CK(dmalloc(&c->digits, (ent + 16) * 4, &acc));
+  CK(dmalloc(&c->ranks, (ent + 16) * 4, &acc));
   CK(dmalloc(&c->buckets, (size_t)p.nb_total * xyzz, &acc));
   // chunks(n) = ceil(n*W / K(n)) <= max(148*512*8 (+slack), ceil(max_n*W/128))  -- see pick_K
   size_t mc = std::max<size_t>(700000, (ent + 127) / 128 + 1);
@@ -174,12 +178,39 @@ static int ctx_alloc(gmsm_ctx* c) {
   for (int i = 0; i < 9; i++) CK(cudaEventCreate(&c->ev[i]));
   CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_split[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   return GMSM_OK;
+}
+
+// Point gathers are 64-byte random reads: while an engine context lives on a device, L2 is kept from promoting them to
+// 128-byte fetches (measured: DRAM traffic of the bucket pass 32.4 -> 17.2 GB).  The limit is a per-device setting of the
+// whole process, so it is reference-counted and the previous value restored when the last context of the device goes away
+// (GMSM_L2_FETCH=0 leaves the limit alone).
+static std::mutex g_l2_mu;
+static std::map<int, std::pair<int, size_t>> g_l2_state;   // device -> (live contexts, previous limit)
+static void l2_granularity_acquire(int device) {
+  if (const char* e = getenv("GMSM_L2_FETCH")) if (atoi(e) == 0) return;
+  std::lock_guard<std::mutex> lk(g_l2_mu);
+  auto& st = g_l2_state[device];
+  if (st.first++ == 0) {
+    size_t prev = 0;
+    if (cudaDeviceGetLimit(&prev, cudaLimitMaxL2FetchGranularity) != cudaSuccess) { cudaGetLastError(); prev = 0; }
+    st.second = prev;
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) != cudaSuccess) cudaGetLastError();
+  }
+}
+static void l2_granularity_release(int device) {
+  if (const char* e = getenv("GMSM_L2_FETCH")) if (atoi(e) == 0) return;
+  std::lock_guard<std::mutex> lk(g_l2_mu);
+  auto it = g_l2_state.find(device);
+  if (it == g_l2_state.end() || it->second.first == 0) return;
+  if (--it->second.first == 0 && it->second.second)
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, it->second.second) != cudaSuccess) cudaGetLastError();
 }
 
 static void ctx_free(gmsm_ctx* c) {
   cudaSetDevice(c->device);
-  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->buckets2); cudaFree(c->buckets);
+  cudaFree(c->hist); cudaFree(c->offsets); cudaFree(c->block_sums); cudaFree(c->entries); cudaFree(c->digits); cudaFree(c->ranks); cudaFree(c->buckets2); cudaFree(c->buckets);
   for (int i = 0; i < 2; i++) { cudaFree(c->carries[i]); cudaFree(c->carry_ids[i]); cudaFree(c->seg[i]); }
   cudaFree(c->win_partials); cudaFree(c->fin_scratch);
   for (int i = 0; i < 2; i++) { cudaFree(c->aff_buf[i]); cudaFree(c->aff_off[i]); }
@@ -189,6 +220,8 @@ static void ctx_free(gmsm_ctx* c) {
   for (int i = 0; i < 9; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; i++) if (c->ev_split[i]) cudaEventDestroy(c->ev_split[i]);
   if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  l2_granularity_release(c->device);
 }
 
 static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int device, bool shared);
@@ -209,8 +242,7 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   if (device < 0 || device >= ndev) { set_err(GMSM_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { set_err(GMSM_ECUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
   if (max_n == 0) max_n = 1;
-  // point gathers are 64-byte random reads: do not let L2 promote them to 128-byte fetches
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  l2_granularity_acquire(device);
   gmsm_ctx* ctx = new gmsm_ctx();
   ctx->curve = curve;
   ctx->device = device;
@@ -225,15 +257,18 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
   if (shared) ctx->affine = false;   // the window-table mode has one accumulation path
   if (const char* e = getenv("GMSM_TABLE_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 256) ctx->table_passes = v; }
+  if (const char* e = getenv("GMSM_QUAD")) ctx->quad_mode = atoi(e);
+  if (const char* e = getenv("GMSM_QUAD_MAX")) { long v = atol(e); if (v >= 0) ctx->quad_max_items = (size_t)v; }
   if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = ctx->split_tab = v; }
   ctx->plan = make_plan(ci.fr_bits, c);
   if (shared) ctx->plan.nb_total = std::max(ctx->plan.nb, ctx->plan.nb_last);   // one bucket set for all windows
   if ((double)max_n * ctx->plan.nwin >= 4294967000.0) {
     set_err(GMSM_EINVAL, "n*W = %zu*%d does not fit the 32-bit entry index; shard the MSM", max_n, ctx->plan.nwin);
+    l2_granularity_release(device);
     delete ctx;
     return nullptr;
   }
-  if (max_n > (1ull << 31) - 1) { set_err(GMSM_EINVAL, "n too large"); delete ctx; return nullptr; }
+  if (max_n > (1ull << 31) - 1) { set_err(GMSM_EINVAL, "n too large"); l2_granularity_release(device); delete ctx; return nullptr; }
   if (ctx_alloc(ctx) != GMSM_OK) { ctx_free(ctx); delete ctx; return nullptr; }
   return ctx;
 }
@@ -261,13 +296,30 @@ extern "C" int gmsm_ctx_last_stage_ms(gmsm_ctx_t* ctx, float out_ms[8]) {
   return GMSM_OK;
 }
 
+// Device-level entry points share one workspace per context and are asynchronous: `CtxCall` holds the context mutex while
+// a call is ENQUEUED and chains the calls on the GPU through ctx->ev_done (the call's stream first waits for the previous
+// call's completion event, and records it again at the end), so that calls issued from different streams or threads run
+// one after the other instead of overlapping on hist / digits / entries / buckets / carries.
+struct CtxCall {
+  gmsm_ctx* c;
+  cudaStream_t st;
+  std::unique_lock<std::mutex> lk;
+  CtxCall(gmsm_ctx* ctx, cudaStream_t s) : c(ctx), st(s), lk(ctx->mu) {}
+  int begin() {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamWaitEvent(st, c->ev_done, 0));
+    return GMSM_OK;
+  }
+  ~CtxCall() { cudaEventRecord(c->ev_done, st); }
+};
+
 extern "C" int gmsm_ctx_window_sums_device(gmsm_ctx_t* ctx, const void* d_points, const void* d_scalars, size_t n,
                                            void* d_partials, void* stream) {
   if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
   if (ctx->shared) return set_err(GMSM_EINVAL, "window-table context: use gmsm_ctx_msm_tables_device");
   if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  CK(cudaSetDevice(ctx->device));
+  CtxCall call(ctx, (cudaStream_t)stream);
+  if (int rc0 = call.begin()) return rc0;
   int rc = GMSM_OK;
   rc = vtable(ctx->curve)->window_sums(ctx, d_points, d_scalars, n, d_partials, (cudaStream_t)stream);
   if (rc == GMSM_OK && ctx->profiling) {
@@ -282,8 +334,8 @@ extern "C" int gmsm_ctx_finalize_device(gmsm_ctx_t* ctx, const void* d_partials,
                                         void* stream) {
   if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
   if (nranks < 1) return set_err(GMSM_EINVAL, "nranks must be >= 1");
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  CK(cudaSetDevice(ctx->device));
+  CtxCall call(ctx, (cudaStream_t)stream);
+  if (int rc0 = call.begin()) return rc0;
   int rc = GMSM_OK;
   rc = vtable(ctx->curve)->finalize(ctx, d_partials, nranks, d_out_jac, (cudaStream_t)stream);
   return rc;
@@ -294,8 +346,8 @@ extern "C" int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const 
   if (!ctx) return set_err(GMSM_EINVAL, "null ctx");
   if (ctx->shared) return set_err(GMSM_EINVAL, "window-table context: use gmsm_ctx_msm_tables_device");
   if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  CK(cudaSetDevice(ctx->device));
+  CtxCall call(ctx, (cudaStream_t)stream);
+  if (int rc0 = call.begin()) return rc0;
   int rc = GMSM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   rc = vtable(ctx->curve)->window_sums(ctx, d_points, d_scalars, n, ctx->win_partials, st);
@@ -311,6 +363,18 @@ extern "C" int gmsm_ctx_msm_device(gmsm_ctx_t* ctx, const void* d_points, const 
   return GMSM_OK;
 }
 
+// make the device that owns a device pointer current (entry points that take raw device pointers and no context:
+// a process driving several GPUs must not depend on the caller's current device)
+static int set_device_of(const void* dptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, dptr) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) {
+    CK(cudaSetDevice(a.device));
+  } else {
+    cudaGetLastError();
+  }
+  return GMSM_OK;
+}
+
 // ---- window tables (device level) ----
 extern "C" int gmsm_tables_build_device(gmsm_curve_t curve, int c, const void* d_points, size_t n, void* d_table,
                                         size_t row_stride, void* stream) {
@@ -322,6 +386,7 @@ extern "C" int gmsm_tables_build_device(gmsm_curve_t curve, int c, const void* d
   if ((double)row_stride * p.nwin >= 2147483000.0)
     return set_err(GMSM_EINVAL, "row_stride*W = %zu*%d does not fit the 31-bit table index; shard the bases", row_stride, p.nwin);
   if (n == 0) return GMSM_OK;
+  if (int rc = set_device_of(d_table)) return rc;
   const size_t ab = 8u * ci.coord_words;
   cudaStream_t st = (cudaStream_t)stream;
   if (d_table != d_points) CK(cudaMemcpyAsync(d_table, d_points, n * ab, cudaMemcpyDeviceToDevice, st));
@@ -339,8 +404,8 @@ extern "C" int gmsm_ctx_msm_tables_device(gmsm_ctx_t* ctx, const void* d_table, 
   if (n > ctx->max_n) return set_err(GMSM_EINVAL, "n=%zu exceeds ctx capacity %zu", n, ctx->max_n);
   if (offset > row_stride || n > row_stride - offset) return set_err(GMSM_EINVAL, "len(points) != len(scalars)");
   if ((double)row_stride * ctx->plan.nwin >= 2147483000.0) return set_err(GMSM_EINVAL, "row_stride*W does not fit the 31-bit table index");
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  CK(cudaSetDevice(ctx->device));
+  CtxCall call(ctx, (cudaStream_t)stream);
+  if (int rc0 = call.begin()) return rc0;
   cudaStream_t st = (cudaStream_t)stream;
   ctx->tab_stride = (uint32_t)row_stride;
   const size_t ab = 8u * ctx->ci.coord_words;
@@ -355,6 +420,130 @@ extern "C" int gmsm_ctx_msm_tables_device(gmsm_ctx_t* ctx, const void* d_table, 
     ctx->have_stage = true;
   }
   return GMSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host staging: pageable caller memory -> pinned ring -> device
+// ------------------------------------------------------------------------------------------
+// A Go caller hands over ordinary (pageable) slices (cgo pins them only for the duration of the call and
+// the library must not keep them).  cudaMemcpyAsync from pageable memory is staged by the driver through one bounce buffer,
+// synchronously on the calling thread, at a fraction of the PCIe rate.  The library therefore stages such buffers itself:
+// a few host threads copy 8 MiB pieces into a ring of pinned slots, each slot is sent with a true asynchronous H2D copy as
+// soon as it is full, and the calling thread moves on to fill the next slot -- memcpy, PCIe and the GPU's bucket pass of
+// the previous batch all overlap.  Buffers that are already pinned / registered (cudaPointerGetAttributes) skip the ring.
+class CopyPool {
+ public:
+  static CopyPool& get() {
+    static CopyPool* p = new CopyPool();   // leaked on purpose: worker threads must not be joined from a static destructor
+    return *p;
+  }
+  // dst[0..n) = src[0..n), split over the pool; blocks until done.  One job at a time (the phases are bandwidth-bound).
+  void copy(char* dst, const char* src, size_t n) {
+    if (nthreads_ <= 1 || n < (size_t)(2 << 20)) { memcpy(dst, src, n); return; }
+    std::lock_guard<std::mutex> run(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      d_ = dst; s_ = src; n_ = n;
+      parts_ = (int)((n + PART - 1) / PART);
+      next_.store(0);
+      remaining_.store(parts_);
+      gen_++;
+    }
+    cv_work_.notify_all();
+    work();   // the caller takes parts too
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return remaining_.load() == 0; });
+  }
+  int threads() const { return nthreads_; }
+
+ private:
+  static constexpr size_t PART = 1 << 20;
+  CopyPool() {
+    int hw = (int)std::thread::hardware_concurrency();
+    nthreads_ = std::max(1, std::min(8, hw / 4));
+    if (const char* e = getenv("GMSM_COPY_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nthreads_ = v; }
+    for (int i = 1; i < nthreads_; i++) std::thread([this] { loop(); }).detach();
+  }
+  void work() {
+    for (;;) {
+      const int k = next_.fetch_add(1);
+      if (k >= parts_) return;
+      const size_t off = (size_t)k * PART, len = std::min(PART, n_ - off);
+      memcpy(d_ + off, s_ + off, len);
+      if (remaining_.fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> lk(mu_);
+        cv_done_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+      }
+      work();
+    }
+  }
+  int nthreads_ = 1;
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  uint64_t gen_ = 0;
+  char* d_ = nullptr;
+  const char* s_ = nullptr;
+  size_t n_ = 0;
+  int parts_ = 0;
+  std::atomic<int> next_{0}, remaining_{0};
+};
+
+struct Stager {
+  static constexpr size_t SLOT = 8u << 20;
+  static constexpr int NSLOT = 4;
+  char* slot[NSLOT] = {};
+  cudaEvent_t ev[NSLOT] = {};
+  bool used[NSLOT] = {};
+  int next = 0;
+  int init() {
+    if (slot[0]) return GMSM_OK;
+    for (int i = 0; i < NSLOT; i++) {
+      CK(cudaMallocHost((void**)&slot[i], SLOT));
+      CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    return GMSM_OK;
+  }
+  void release() {
+    for (int i = 0; i < NSLOT; i++) {
+      if (slot[i]) cudaFreeHost(slot[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      slot[i] = nullptr; ev[i] = nullptr; used[i] = false;
+    }
+  }
+  // pageable src -> device dst on stream st through the ring
+  int copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (int rc = init()) return rc;
+    const char* s = reinterpret_cast<const char*>(src);
+    char* d = reinterpret_cast<char*>(dst);
+    for (size_t off = 0; off < bytes; off += SLOT) {
+      const size_t len = std::min(SLOT, bytes - off);
+      const int k = next;
+      next = (next + 1) % NSLOT;
+      if (used[k]) CK(cudaEventSynchronize(ev[k]));   // the slot's previous H2D has left the host buffer
+      CopyPool::get().copy(slot[k], s + off, len);
+      CK(cudaMemcpyAsync(d + off, slot[k], len, cudaMemcpyHostToDevice, st));
+      CK(cudaEventRecord(ev[k], st));
+      used[k] = true;
+    }
+    return GMSM_OK;
+  }
+};
+
+// is this host pointer pinned (cudaMallocHost / cudaHostRegister) or managed, i.e. safe for a truly asynchronous copy?
+static bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -378,6 +567,8 @@ struct Pipeline {
   bool tables = false;
   size_t tab_stride = 0;
   int tab_c = 0;
+  Stager stager;          // pinned ring for pageable caller buffers
+  int last_staged = 0;    // 1 if the last call went through the ring
 };
 
 static int pipeline_init(Pipeline& P, int curve, int device) {
@@ -392,6 +583,7 @@ static int pipeline_init(Pipeline& P, int curve, int device) {
 
 static void pipeline_free(Pipeline& P) {
   if (P.ctx) gmsm_ctx_destroy(P.ctx);
+  P.stager.release();
   cudaFree(P.d_scalars); cudaFree(P.d_partials); cudaFree(P.d_out);
   if (P.copy_st) cudaStreamDestroy(P.copy_st);
   if (P.comp_st) cudaStreamDestroy(P.comp_st);
@@ -476,11 +668,35 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   }
   int launches = 0;
   std::lock_guard<std::mutex> lk(P.ctx->mu);
+  // Every exit path -- success or error -- leaves with the copy, compute and auxiliary streams drained: the caller's host
+  // buffers (and, on the next call, this pipeline's device buffers) may be reused or freed as soon as we return
+  // (SURVEY.md section 8b "finish all reads before returning").
+  struct Drain {
+    Pipeline& P;
+    ~Drain() {
+      cudaStreamSynchronize(P.copy_st);
+      cudaStreamSynchronize(P.comp_st);
+      if (P.ctx && P.ctx->aux) cudaStreamSynchronize(P.ctx->aux);
+    }
+  } drain{P};
+  // pageable caller buffers go through the pinned ring (GMSM_STAGING=0: hand them to cudaMemcpyAsync as they are)
+  bool staging = true;
+  if (const char* e = getenv("GMSM_STAGING")) staging = atoi(e) != 0;
+  const bool stage_scalars = staging && n * 32 >= (1u << 20) && !host_pointer_is_pinned(hs);
+  const bool stage_points = staging && hp && n * ab >= (1u << 20) && !host_pointer_is_pinned(hp);
+  P.last_staged = (stage_scalars || stage_points) ? 1 : 0;
+  auto h2d = [&](void* dst, const char* src, size_t bytes, bool staged) -> int {
+    if (staged) return P.stager.copy(dst, src, bytes, P.copy_st);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, P.copy_st));
+    return GMSM_OK;
+  };
+  int fault_after = -1;   // test hook: fail after the given batch has been enqueued (the streams are then busy)
+  if (const char* e = getenv("GMSM_FAULT_AFTER_BATCH")) fault_after = atoi(e);
   for (int k = 0; k < nch; k++) {
     const size_t off = bstart[k];
     const size_t m = bstart[k + 1] - off;
-    CK(cudaMemcpyAsync((char*)P.d_scalars + off * 32, hs + off * 32, m * 32, cudaMemcpyHostToDevice, P.copy_st));
-    if (hp) CK(cudaMemcpyAsync((char*)d_points + off * ab, hp + off * ab, m * ab, cudaMemcpyHostToDevice, P.copy_st));
+    if (int rc = h2d((char*)P.d_scalars + off * 32, hs + off * 32, m * 32, stage_scalars)) return rc;
+    if (hp) if (int rc = h2d((char*)d_points + off * ab, hp + off * ab, m * ab, stage_points)) return rc;
     CK(cudaEventRecord(P.ev[k], P.copy_st));
     CK(cudaStreamWaitEvent(P.comp_st, P.ev[k], 0));
     int rc;
@@ -492,6 +708,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     }
     if (rc) return rc;
     launches += P.ctx->last_launches;
+    if (k == fault_after) return set_err(GMSM_ECUDA, "injected fault after batch %d (GMSM_FAULT_AFTER_BATCH)", k);
   }
   if (shared_buckets) {
     P.ctx->last_launches = 0;
@@ -500,7 +717,6 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     if (h_partials) {
       CK(cudaMemcpyAsync(h_partials, P.d_partials, (size_t)npart * xb, cudaMemcpyDeviceToHost, P.comp_st));
       CK(cudaStreamSynchronize(P.comp_st));
-      CK(cudaStreamSynchronize(P.copy_st));
       P.last_launches = launches;
       return GMSM_OK;
     }
@@ -511,7 +727,6 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   P.last_launches = launches + 1;
   CK(cudaMemcpyAsync(out_jac, P.d_out, jb, cudaMemcpyDeviceToHost, P.comp_st));
   CK(cudaStreamSynchronize(P.comp_st));
-  CK(cudaStreamSynchronize(P.copy_st));
   g_last_oneshot_launches = P.last_launches;
   return GMSM_OK;
 }
@@ -741,24 +956,66 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   return join_partials(b->curve, s0.pipe, &s0.d_gather, &s0.gather_cap, h_part.data(), h_part.size(), (int)jobs.size(), out_jac);
 }
 
-// per-(curve, device) session of the host entry points: device buffers, streams and the engine context are kept
-// between calls (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc
-struct Session { Pipeline pipe; void* d_points = nullptr; size_t cap = 0; void* d_gather = nullptr; size_t gather_cap = 0; };
+// Sessions of the host entry points: device buffers, streams, the pinned ring and the engine context are kept between
+// calls (grow-only, shrunk when 4x oversized) so a call costs its copies and kernels, not cudaMalloc.  Each (curve, device)
+// pair owns a small POOL of sessions (GMSM_SESSIONS, default 3): a call leases a free one, so concurrent calls -- gnark's
+// provers run several MultiExp at once, BenchmarkManyMultiExpG1Reference multiexp_test.go:385-415 -- on different curves,
+// different devices or even the same pair proceed in parallel (the H2D of one under the bucket pass of another); a call
+// waits only when every session of its pair is taken.  The global mutex guards the table, never a call.
+struct Session {
+  Pipeline pipe;
+  void* d_points = nullptr;
+  size_t cap = 0;
+  void* d_gather = nullptr;
+  size_t gather_cap = 0;
+  bool busy = false;
+};
 static std::mutex g_sess_mu;
-static std::map<std::pair<int, int>, Session> g_sessions;
+static std::condition_variable g_sess_cv;
+static std::map<std::pair<int, int>, std::vector<std::unique_ptr<Session>>> g_sessions;
 
-static int session_prepare(int curve, int device, size_t cnt, Session** out) {
+static int session_pool_size() {
+  int v = 3;
+  if (const char* e = getenv("GMSM_SESSIONS")) v = atoi(e);
+  return std::max(1, std::min(v, 16));
+}
+
+struct SessionLease {
+  Session* S = nullptr;
+  SessionLease() = default;
+  SessionLease(const SessionLease&) = delete;
+  SessionLease& operator=(const SessionLease&) = delete;
+  SessionLease(SessionLease&& o) noexcept : S(o.S) { o.S = nullptr; }
+  void acquire(int curve, int device) {
+    std::unique_lock<std::mutex> lk(g_sess_mu);
+    auto& pool = g_sessions[std::make_pair(curve, device)];
+    const size_t cap = (size_t)session_pool_size();
+    for (;;) {
+      for (auto& u : pool) if (!u->busy) { S = u.get(); break; }
+      if (!S && pool.size() < cap) { pool.emplace_back(new Session()); S = pool.back().get(); }
+      if (S) break;
+      g_sess_cv.wait(lk);
+    }
+    S->busy = true;
+  }
+  ~SessionLease() {
+    if (!S) return;
+    { std::lock_guard<std::mutex> lk(g_sess_mu); S->busy = false; }
+    g_sess_cv.notify_one();
+  }
+};
+
+// size the leased session's point buffer for cnt points (exclusive access: the lease)
+static int session_prepare(Session& S, int curve, int device, size_t cnt) {
   CurveInfo ci;
   curve_info(curve, &ci);
   CK(cudaSetDevice(device));
-  Session& S = g_sessions[std::make_pair(curve, device)];
   if (int rc = pipeline_init(S.pipe, curve, device)) return rc;
   if (S.cap < cnt || S.cap > 4 * cnt + 1024) {
     cudaFree(S.d_points); S.d_points = nullptr; S.cap = 0;
     CK(cudaMalloc(&S.d_points, cnt * 8u * ci.coord_words));
     S.cap = cnt;
   }
-  *out = &S;
   return GMSM_OK;
 }
 
@@ -778,10 +1035,10 @@ extern "C" int gmsm_multiexp_window_sums(gmsm_curve_t curve, const uint64_t* poi
   if (int rc = check_device(device)) return rc;
   const WindowPlan plan = make_plan(ci.fr_bits, c);
   if (n == 0) { memset(out_partials, 0, (size_t)plan.nwin * 16u * ci.coord_words); return GMSM_OK; }
-  std::lock_guard<std::mutex> lk(g_sess_mu);
-  Session* S = nullptr;
-  if (int rc = session_prepare(curve, device, n, &S)) return rc;
-  return pipeline_run(S->pipe, S->d_points, points, scalars, n, nullptr, c, out_partials);
+  SessionLease lease;
+  lease.acquire(curve, device);
+  if (int rc = session_prepare(*lease.S, curve, device, n)) return rc;
+  return pipeline_run(lease.S->pipe, lease.S->d_points, points, scalars, n, nullptr, c, out_partials);
 }
 
 extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
@@ -799,33 +1056,34 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   }
   for (int d : devs) if (int rc = check_device(d)) return rc;
   if (n == 0) { memset(out_jac, 0, 12u * ci.coord_words); return GMSM_OK; }
-  std::lock_guard<std::mutex> lk(g_sess_mu);
   const size_t ab = 8u * ci.coord_words;
-  auto prepare = [&](int device, size_t cnt, Session** out) -> int { return session_prepare(curve, device, cnt, out); };
   const size_t D = (n >= ((size_t)1 << 16)) ? devs.size() : 1;   // small calls stay on one device
   if (D == 1) {
-    Session* S = nullptr;
-    if (int rc = prepare(devs[0], n, &S)) return rc;
-    return pipeline_run(S->pipe, S->d_points, points, scalars, n, out_jac);
+    SessionLease lease;
+    lease.acquire(curve, devs[0]);
+    if (int rc = session_prepare(*lease.S, curve, devs[0], n)) return rc;
+    return pipeline_run(lease.S->pipe, lease.S->d_points, points, scalars, n, out_jac);
   }
   // ---- multi-device: contiguous shards (the reference's recursive halving, multiexp.go:128-140) ----
   const int c = choose_c(ci.fr_bits, n);
   const WindowPlan plan = make_plan(ci.fr_bits, c);
-  const size_t xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
+  const size_t xb = 16u * ci.coord_words;
   std::vector<unsigned char> h_part(D * plan.nwin * xb);
   std::vector<int> rcs(D, GMSM_OK);
   std::vector<std::string> errs(D);
-  std::vector<Session*> ss(D, nullptr);
+  std::vector<SessionLease> leases(D);
   for (size_t d = 0; d < D; d++) {
     const size_t lo = n * d / D, hi = n * (d + 1) / D;
-    if (int rc = prepare(devs[d], hi - lo, &ss[d])) return rc;
+    leases[d].acquire(curve, devs[d]);
+    if (int rc = session_prepare(*leases[d].S, curve, devs[d], hi - lo)) return rc;
   }
   {
     std::vector<std::thread> th;
     for (size_t d = 0; d < D; d++) {
       th.emplace_back([&, d]() {
         const size_t lo = n * d / D, hi = n * (d + 1) / D;
-        rcs[d] = pipeline_run(ss[d]->pipe, ss[d]->d_points, points + lo * (ab / 8), scalars + lo * 4, hi - lo, nullptr, c,
+        Session& S = *leases[d].S;
+        rcs[d] = pipeline_run(S.pipe, S.d_points, points + lo * (ab / 8), scalars + lo * 4, hi - lo, nullptr, c,
                               h_part.data() + d * plan.nwin * xb);
         if (rcs[d]) errs[d] = g_err;   // thread-local error text of the worker
       });
@@ -835,10 +1093,10 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
   for (size_t d = 0; d < D; d++)
     if (rcs[d]) return set_err(rcs[d], "device %d: %s", devs[d], errs[d].c_str());
   // join on the first device: per-window sum over the D shards, Horner, normalisation
-  Session& S0 = *ss[0];
+  Session& S0 = *leases[0].S;
   if (int rc = join_partials(curve, S0.pipe, &S0.d_gather, &S0.gather_cap, h_part.data(), h_part.size(), (int)D, out_jac)) return rc;
   int launches = 1;
-  for (size_t d = 0; d < D; d++) launches += ss[d]->pipe.last_launches;
+  for (size_t d = 0; d < D; d++) launches += leases[d].S->pipe.last_launches;
   g_last_oneshot_launches = launches;
   return GMSM_OK;
 }
@@ -858,6 +1116,7 @@ extern "C" int gmsm_generate_multiples_device(gmsm_curve_t curve, const uint64_t
   CurveInfo ci;
   if (!curve_info(curve, &ci)) return set_err(GMSM_EINVAL, "unknown curve id %d", (int)curve);
   if (n == 0) return GMSM_OK;
+  if (int rc = set_device_of(d_out_points)) return rc;
   void* d_base = nullptr;
   const size_t ab = 8u * ci.coord_words;
   CK(cudaMalloc(&d_base, ab));

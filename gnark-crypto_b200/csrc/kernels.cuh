@@ -3,7 +3,7 @@
 // Pipeline (replaces ecc/bn254/multiexp.go:148-209 `_innerMsmG1` and its callees):
 //   K1  k_digits_hist      partitionScalars (multiexp.go:709-803) fused with a bucket histogram
 //   K1b k_scan_*           exclusive scan of the histogram -> bucket offsets
-//   K1c k_digits_scatter   partitionScalars again (recomputed, not stored) -> entries grouped by bucket
+//   K1c k_scatter_window   digits + ranks -> entries grouped by bucket (no atomics: K1 numbered them)
 //   K2  k_accumulate       bucket accumulation (processChunk, multiexp_jacobian.go:20-39) as a
 //                          load-balanced segmented reduction over the bucket-ordered entry list
 //   K2b k_carry_level      joins partial sums of buckets that span several chunks
@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "groups.cuh"
+#include "quad.cuh"
 #include "testops.cuh"
 
 namespace gmsm {
@@ -92,17 +93,40 @@ template <class F>
 __device__ __noinline__ XYZZ<F> xyzz_double_cold(const XYZZ<F>& q) {
   return xyzz_double(q);
 }
+// lane-parallel twins (quad.cuh): one point operation per QUAD of lanes
+template <class F>
+__device__ __noinline__ void xyzz_add_quad_cold(Quad q, XYZZ<F>& p, const XYZZ<F>& a) {
+  xyzz_add_quad(q, p, a);
+}
+template <class F>
+__device__ __noinline__ XYZZ<F> xyzz_double_quad_cold(Quad q, const XYZZ<F>& a) {
+  return xyzz_double_quad(q, a);
+}
+// The tail kernels below exist in two forms selected by the template flag Q: Q = false, one thread per work item (serial
+// chain); Q = true, one quad per work item (4x the threads, ~3x shorter chains).  The host picks Q = true whenever the
+// 4x grid still fits the machine in about one wave -- these stages are then bound by the latency of the chain, not by
+// the multiplier pipe.
+template <bool Q, class F>
+GMSM_D void tail_add(const Quad& q, XYZZ<F>& p, const XYZZ<F>& a) {
+  if constexpr (Q) xyzz_add_quad_cold(q, p, a); else xyzz_add_cold(p, a);
+}
+template <bool Q, class F>
+GMSM_D XYZZ<F> tail_double(const Quad& q, const XYZZ<F>& a) {
+  if constexpr (Q) return xyzz_double_quad_cold(q, a); else return xyzz_double_cold(a);
+}
 
 // ------------------------------------------------------------------------------------------
 // K1: signed-digit recoding.  Calls fn(window, magnitude >= 1, sign) for every non-zero digit.
 // Semantics of partitionScalars (multiexp.go:743-800): zero scalars skipped; digit = carry + c bits;
 // windows 0..W-2 borrow (digit > 2^(c-1)-1 -> digit -= 2^c, carry 1); last window never borrows.
 // ------------------------------------------------------------------------------------------
-template <class G, class Fn>
+// SHORTCUT = false drops the early exit for zero scalars (they then walk the loop and produce the same all-zero digits):
+// callers that use warp-collective operations inside fn need every lane in the same iteration.
+template <class G, bool SHORTCUT = true, class Fn>
 GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn) {
   using Fr = typename G::Fr;
   constexpr int N = Fr::N;
-  if (s_mont.is_zero()) {                 // IsZero() on the Montgomery limbs, multiexp.go:743
+  if (SHORTCUT && s_mont.is_zero()) {     // IsZero() on the Montgomery limbs, multiexp.go:743
     for (int j = 0; j < nwin; j++) fn(j, 0u);
     return;
   }
@@ -141,69 +165,83 @@ GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn)
 // bucket index inside its window for a non-zero code: magnitude - 1
 GMSM_D uint32_t code_bucket(uint32_t code) { return (code >> 1) - 1u + (code & 1u); }
 
-// K1: digits (stored chunk-major, digits[j*n + i], the reference's layout multiexp.go:785) + histogram
+// K1: digits (stored chunk-major, digits[j*n + i], the reference's layout multiexp.go:785) + histogram + the RANK of every
+// entry inside its bucket (ranks[j*n + i]): the returning atomicAdd that counts the bucket also numbers its entries, so
+// the scatter (K1c) needs no atomics at all.  The atomics are warp-aggregated: lanes of a warp that hit the same bucket
+// (__match_any_sync) send ONE atomicAdd of their count and number themselves locally.  Skewed inputs -- the reference's
+// "redundancy" benchmark (runs of 100 equal scalars) or "smallvalues" (n/5 equal scalars), multiexp_test.go:316-334 --
+// otherwise put millions of atomics on a handful of addresses; here all W hot addresses of such an input are in flight at
+// once (one kernel for all windows) instead of one per scatter launch.
+// The loop is block-uniform and lanes past the end walk it with a zero scalar: every lane of a warp reaches the collectives.
 template <class G>
 __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
-                              uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    typename G::Fr s = load_vec_ro(scalars + i);
-    for_each_digit<G>(s, c, nwin, [&](int j, uint32_t code) {
-      digits[(size_t)j * n + i] = code;
-      if (code) atomicAdd(&hist[(uint32_t)j * nb + code_bucket(code)], 1u);
+                              uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ ranks, uint32_t* __restrict__ hist) {
+  using Fr = typename G::Fr;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i64 = base + threadIdx.x;
+    const bool valid = i64 < n;
+    const uint32_t i = (uint32_t)i64;
+    Fr s = Fr::zero();
+    if (valid) s = load_vec_ro(scalars + i);
+    for_each_digit<G, false>(s, c, nwin, [&](int j, uint32_t code) {
+      const uint32_t key = code ? (uint32_t)j * nb + code_bucket(code) : ID_NONE;
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (code) {
+        const int leader = __ffs((int)peers) - 1;
+        uint32_t first = 0;
+        if ((int)lane == leader) first = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+        first = __shfl_sync(peers, first, leader);
+        ranks[(size_t)j * n + i] = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      }
+      if (valid) digits[(size_t)j * n + i] = code;
     });
   }
 }
 
-// K1c: scatter of ONE window.  Launched window by window so that the randomly written slice of
-// `entries` (<= 4n bytes) and the window's counters stay L2-resident (126 MB) and reach HBM once, as
-// full lines, instead of one read-modify-write per 4-byte store.  Entries of a bucket are filled from
-// the back: pos = offsets[b] + (old count - 1); the histogram counts down to zero.
-static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t* __restrict__ hist_w,
+// K1c: scatter of ONE window, no atomics: entries[offsets[b] + rank] = (i << 1) | sign.  Launched window by window so that
+// the randomly written slice of `entries` (<= 4n bytes) stays L2-resident (126 MB) and reaches HBM once, as full lines,
+// instead of one read-modify-write per 4-byte store.
+static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, const uint32_t* __restrict__ ranks_w, uint32_t n,
                                         const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries) {
-  // 4 independent elements per thread and iteration: the kernel is bound by the round trip of the
-  // returning atomics (ncu: long_scoreboard 324 per issue with one in flight), so keep 4 in flight
-  constexpr int U = 4;
+  constexpr int U = 4;   // independent elements per thread and iteration
   const uint32_t tile = blockDim.x * U;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n; base += (uint64_t)gridDim.x * tile) {
-    uint32_t code[U], old[U], off[U];
+    uint32_t code[U], rk[U], off[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
       code[u] = (i < n) ? __ldg(digits_w + i) : 0u;
+      rk[u] = (i < n) ? __ldg(ranks_w + i) : 0u;     // (unwritten where code == 0: never used)
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (code[u]) {
-        const uint32_t b = code_bucket(code[u]);
-        old[u] = atomicSub(&hist_w[b], 1u);
-        off[u] = offsets_w[b];
-      }
-    }
+    for (int u = 0; u < U; u++)
+      if (code[u]) off[u] = offsets_w[code_bucket(code[u])];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (code[u]) {
         const uint32_t i = (uint32_t)(base + (uint64_t)u * blockDim.x + threadIdx.x);
-        entries[off[u] + old[u] - 1u] = (i << 1) | (code[u] & 1u);
+        entries[off[u] + rk[u]] = (i << 1) | (code[u] & 1u);
       }
     }
   }
 }
 
 // K1c (window-table mode, see k_table_level): all W windows feed ONE bucket set -- the entry of (scalar i,
-// window j) is the table point j*row_stride + i = 2^(c*j) * P_i, and hist / offsets are indexed by the bucket
+// window j) is the table point j*row_stride + i = 2^(c*j) * P_i, and hist / offsets / ranks are indexed by the bucket
 // alone.  The L2-residency argument of k_scatter_window is kept by passing over the digits once per BUCKET RANGE
 // [blo, bhi): a range owns a contiguous slice of `entries` (~4n bytes for uniform digits), every pass streams
 // all n*W digits (coalesced) and scatters only the ones of its range.  blockIdx.y = window.
-static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, uint32_t n, uint32_t row_stride,
-                                        uint32_t* __restrict__ hist, const uint32_t* __restrict__ offsets,
-                                        uint32_t* __restrict__ entries, uint32_t blo, uint32_t bhi) {
+static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, const uint32_t* __restrict__ ranks, uint32_t n, uint32_t row_stride,
+                                        const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries, uint32_t blo, uint32_t bhi) {
   constexpr int U = 4;
   const uint32_t tile = blockDim.x * U;
   const uint32_t j = blockIdx.y;
   const uint32_t* digits_w = digits + (size_t)j * n;
+  const uint32_t* ranks_w = ranks + (size_t)j * n;
   const uint32_t idx0 = j * row_stride;      // (W * row_stride) < 2^31 is checked by the host
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n; base += (uint64_t)gridDim.x * tile) {
-    uint32_t code[U], old[U], off[U];
+    uint32_t code[U], rk[U], off[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
@@ -212,20 +250,16 @@ static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, uin
         const uint32_t b = code_bucket(code[u]);
         if (b < blo || b >= bhi) code[u] = 0u;
       }
+      rk[u] = code[u] ? __ldg(ranks_w + i) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (code[u]) {
-        const uint32_t b = code_bucket(code[u]);
-        old[u] = atomicSub(&hist[b], 1u);
-        off[u] = offsets[b];
-      }
-    }
+    for (int u = 0; u < U; u++)
+      if (code[u]) off[u] = offsets[code_bucket(code[u])];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (code[u]) {
         const uint32_t i = (uint32_t)(base + (uint64_t)u * blockDim.x + threadIdx.x);
-        entries[off[u] + old[u] - 1u] = ((idx0 + i) << 1) | (code[u] & 1u);
+        entries[off[u] + rk[u]] = ((idx0 + i) << 1) | (code[u] & 1u);
       }
     }
   }
@@ -344,11 +378,14 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 #ifndef GMSM_ACC_MINBLOCKS_BIG
 #define GMSM_ACC_MINBLOCKS_BIG 1
 #endif
+#ifndef GMSM_ACC_MINBLOCKS_SMALL
+#define GMSM_ACC_MINBLOCKS_SMALL 4
+#endif
 #ifndef GMSM_ACC_PREFETCH_BEND
 #define GMSM_ACC_PREFETCH_BEND 1
 #endif
 template <class G>
-__global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? 4 : GMSM_ACC_MINBLOCKS_BIG)
+__global__ void __launch_bounds__(128, (sizeof(typename G::F) <= 32) ? GMSM_ACC_MINBLOCKS_SMALL : GMSM_ACC_MINBLOCKS_BIG)
 k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, uint32_t nb_total, uint32_t K, uint32_t nchunks,
              XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ carries,
@@ -437,13 +474,16 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
 // the items of one bucket are contiguous.  A thread walks K2 consecutive items, sums runs of equal id;
 // a run that starts in this thread's range is owned (bucket[id] += sum, exclusive within a level);
 // a run continued from the previous range is forwarded to the next level.
-template <class G>
+template <class G, bool Q>
 __global__ void __launch_bounds__(128)
 k_carry_level(const XYZZ<typename G::F>* __restrict__ in_pts, const uint32_t* __restrict__ in_ids, uint32_t n_in,
               uint32_t K2, XYZZ<typename G::F>* __restrict__ buckets, XYZZ<typename G::F>* __restrict__ out_pts,
               uint32_t* __restrict__ out_ids) {
   using F = typename G::F;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = Q ? gid >> 2 : gid;
+  const Quad qd = quad_of_thread();
+  const bool writer = !Q || qd.ql == 0;
   const uint32_t n_out = (n_in + K2 - 1) / K2;
   if (t >= n_out) return;
   const uint32_t start = t * K2;
@@ -455,16 +495,17 @@ k_carry_level(const XYZZ<typename G::F>* __restrict__ in_pts, const uint32_t* __
     uint32_t id = (i < end) ? in_ids[i] : ID_NONE;
     if (id == cur && id != ID_NONE) {
       XYZZ<F> q = load_vec(in_pts + i);
-      xyzz_add_cold(acc, q);
+      tail_add<Q>(qd, acc, q);
       continue;
     }
     if (cur != ID_NONE) {  // run ended: flush
       if (owner) {
         XYZZ<F> old = load_vec(buckets + cur);
-        xyzz_add_cold(old, acc);
-        store_vec(buckets + cur, old);
+        if constexpr (Q) __syncwarp(qd.mask);   // every lane of the quad has read the bucket before lane 0 rewrites it
+        tail_add<Q>(qd, old, acc);
+        if (writer) store_vec(buckets + cur, old);
       } else {
-        store_vec(out_pts + t, acc);
+        if (writer) store_vec(out_pts + t, acc);
         out_id = cur;
       }
       cur = ID_NONE;
@@ -475,7 +516,7 @@ k_carry_level(const XYZZ<typename G::F>* __restrict__ in_pts, const uint32_t* __
       owner = !(i == start && start > 0 && in_ids[start - 1] == id);
     }
   }
-  out_ids[t] = out_id;
+  if (writer) out_ids[t] = out_id;
 }
 
 // dst[b] += src[b] for every bucket (joins the buckets of a pipelined batch into the running ones)
@@ -499,18 +540,21 @@ k_merge_buckets(XYZZ<typename G::F>* __restrict__ dst, const XYZZ<typename G::F>
 // each thread also applies the small scalar sL by double-and-add, so segments are independent and the
 // window total is a plain sum of the segment results (k_sum_groups).
 // ------------------------------------------------------------------------------------------
-template <class G>
+template <class G, bool Q>
 __global__ void __launch_bounds__(128)
 k_bucket_segments(const XYZZ<typename G::F>* __restrict__ buckets, int nwin, uint32_t nb, uint32_t nb_last,
                   uint32_t L, uint32_t S, XYZZ<typename G::F>* __restrict__ seg_out) {
   using F = typename G::F;
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = Q ? tid >> 2 : tid;
+  const Quad qd = quad_of_thread();
+  const bool writer = !Q || qd.ql == 0;
   if (gid >= (uint32_t)nwin * S) return;
   const uint32_t j = gid / S, s = gid % S;
   const uint32_t nbj = (j == (uint32_t)nwin - 1) ? nb_last : nb;
   const uint32_t lo = s * L;
   if (lo >= nbj) {
-    store_vec(seg_out + gid, XYZZ<F>::inf());
+    if (writer) store_vec(seg_out + gid, XYZZ<F>::inf());
     return;
   }
   const uint32_t hi = (nbj - lo < L) ? nbj : lo + L;
@@ -518,27 +562,29 @@ k_bucket_segments(const XYZZ<typename G::F>* __restrict__ buckets, int nwin, uin
   XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
   for (uint32_t k = hi; k-- > lo;) {
     XYZZ<F> bk = load_vec(base + k);
-    xyzz_add_cold(run, bk);
-    xyzz_add_cold(tot, run);
+    tail_add<Q>(qd, run, bk);
+    tail_add<Q>(qd, tot, run);
   }
   if (lo > 0 && !run.is_inf()) {
     XYZZ<F> acc = XYZZ<F>::inf();
     for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-      acc = xyzz_double_cold(acc);
-      if ((lo >> bit) & 1u) xyzz_add_cold(acc, run);
+      acc = tail_double<Q>(qd, acc);
+      if ((lo >> bit) & 1u) tail_add<Q>(qd, acc, run);
     }
-    xyzz_add_cold(tot, acc);
+    tail_add<Q>(qd, tot, acc);
   }
-  store_vec(seg_out + gid, tot);
+  if (writer) store_vec(seg_out + gid, tot);
 }
 
 // out[j][g] = sum_{i in [gR, gR+R)} in[j][i]
-template <class G>
+template <class G, bool Q>
 __global__ void __launch_bounds__(128)
 k_sum_groups(const XYZZ<typename G::F>* __restrict__ in, uint32_t in_per_win, uint32_t R, uint32_t out_per_win,
              int nwin, XYZZ<typename G::F>* __restrict__ out) {
   using F = typename G::F;
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = Q ? tid >> 2 : tid;
+  const Quad qd = quad_of_thread();
   if (gid >= (uint32_t)nwin * out_per_win) return;
   const uint32_t j = gid / out_per_win, g = gid % out_per_win;
   uint32_t lo = g * R, hi = lo + R;
@@ -546,40 +592,48 @@ k_sum_groups(const XYZZ<typename G::F>* __restrict__ in, uint32_t in_per_win, ui
   XYZZ<F> acc = XYZZ<F>::inf();
   for (uint32_t i = lo; i < hi; i++) {
     XYZZ<F> q = load_vec(in + (size_t)j * in_per_win + i);
-    xyzz_add_cold(acc, q);
+    tail_add<Q>(qd, acc, q);
   }
-  store_vec(out + (size_t)j * out_per_win + g, acc);
+  if (!Q || qd.ql == 0) store_vec(out + (size_t)j * out_per_win + g, acc);
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: finalize (one warp).  partials[r][j], r < nranks, j < nwin.
+// K4: finalize (one block of FIN_THREADS).  partials[r][j], r < nranks, j < nwin.  Quads sum over the ranks, window-parallel;
+// then quad 0 runs the Horner chain -- c * (W - 1) dependent doublings, the longest serial chain of an MSM -- with the
+// lane-parallel formulas of quad.cuh (three product steps per doubling instead of seven).
 // ------------------------------------------------------------------------------------------
+static constexpr int FIN_THREADS = 64;
+template <class F>
+__device__ __noinline__ Jac<F> jac_double_quad_cold(Quad q, const Jac<F>& p) {
+  return jac_double_quad(q, p);
+}
 template <class G>
-__global__ void k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int nranks, int nwin, int c,
-                           XYZZ<typename G::F>* __restrict__ scratch /* nwin */, Jac<typename G::F>* __restrict__ out) {
+__global__ void __launch_bounds__(FIN_THREADS)
+k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int nranks, int nwin, int c,
+           XYZZ<typename G::F>* __restrict__ scratch /* nwin */, Jac<typename G::F>* __restrict__ out) {
   using F = typename G::F;
-  // lanes sum over ranks, window-parallel
-  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+  const Quad qd = quad_of_thread();
+  for (int j = threadIdx.x >> 2; j < nwin; j += blockDim.x >> 2) {
     XYZZ<F> acc = load_vec(partials + j);
     for (int r = 1; r < nranks; r++) {
       XYZZ<F> q = load_vec(partials + (size_t)r * nwin + j);
-      xyzz_add_cold(acc, q);
+      xyzz_add_quad_cold(qd, acc, q);
     }
-    store_vec(scratch + j, acc);
+    if (qd.ql == 0) store_vec(scratch + j, acc);
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x >= 4) return;
   // Horner over the windows, high -> low: acc = 2^c * acc + T_j.  The c doublings run in Jacobian
   // coordinates (2M + 5S each instead of 6M + 3S); the addition of T_j in extended Jacobian.
   XYZZ<F> acc = load_vec(scratch + (nwin - 1));
   for (int j = nwin - 2; j >= 0; j--) {
-    Jac<F> dj = xyzz_to_jac(acc);
-    for (int l = 0; l < c; l++) dj = jac_double(dj);
-    acc = jac_to_xyzz(dj);
+    Jac<F> dj = xyzz_to_jac_quad(qd, acc);
+    for (int l = 0; l < c; l++) dj = jac_double_quad_cold(qd, dj);
+    acc = jac_to_xyzz_quad(qd, dj);
     XYZZ<F> q = load_vec(scratch + j);
-    xyzz_add_cold(acc, q);
+    xyzz_add_quad_cold(qd, acc, q);
   }
-  Jac<F> jac = xyzz_to_jac(acc);
+  Jac<F> jac = xyzz_to_jac_quad(qd, acc);
   Affine<F> a = jac_to_affine(jac);
   Jac<F> o;
   if (jac.z.is_zero()) {
@@ -587,7 +641,7 @@ __global__ void k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int
   } else {
     o = Jac<F>{a.x, a.y, F::one()};
   }
-  store_vec(out, o);
+  if (qd.ql == 0) store_vec(out, o);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
+#include <map>
 #include <vector>
 
 #define __global__
@@ -69,6 +70,7 @@ struct Block {
   unsigned bar_arrived = 0, bar_gen = 0;
   unsigned warp_live[32] = {}, warp_arrived[32] = {}, warp_gen[32] = {};
   uint32_t slot[1024] = {};
+  std::map<uint64_t, std::pair<unsigned, unsigned>> grp;   // (warp, mask) -> (arrived, generation): barriers of lane groups
   std::function<void()> body;
 };
 inline Block* g_block = nullptr;   // non-null while a cooperative launch is running
@@ -111,6 +113,29 @@ inline uint32_t shfl(uint32_t v, unsigned src_lane, bool valid) {
   warp_barrier();
   return r;
 }
+// shuffle among the lanes named in `mask` only (the quads of quad.cuh): a barrier over the live lanes of the mask, so that
+// groups of one warp may run different code paths, as independent thread scheduling allows on the hardware
+inline void group_barrier(unsigned w, unsigned /*key*/, uint32_t mask) {
+  Block& B = *g_block;
+  const unsigned base = w << 5;
+  unsigned members = 0;
+  for (unsigned l = 0; l < 32; l++)
+    if (((mask >> l) & 1u) && base + l < B.nthreads && !B.done[base + l]) members++;
+  const uint64_t id = ((uint64_t)w << 32) | mask;     // distinct masks (a quad, a set of peers, the whole warp) never share a counter
+  const unsigned gen = B.grp[id].second;
+  if (++B.grp[id].first >= members) { B.grp[id].first = 0; B.grp[id].second++; return; }
+  while (B.grp[id].second == gen) yield();
+}
+inline uint32_t shfl_masked(uint32_t mask, uint32_t v, unsigned src_lane) {
+  Block& B = *g_block;
+  const unsigned tid = B.cur, base = tid & ~31u, w = tid >> 5, key = (unsigned)__builtin_ctz(mask);
+  assert(((mask >> (tid & 31u)) & 1u) && "calling lane must be named in the mask");
+  B.slot[tid] = v;
+  group_barrier(w, key, mask);
+  const uint32_t r = (base + src_lane < B.nthreads) ? B.slot[base + src_lane] : v;
+  group_barrier(w, key, mask);
+  return r;
+}
 }  // namespace emu
 
 static inline void __syncthreads() {
@@ -125,6 +150,32 @@ static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, int mask) {
   assert(emu::g_block && "warp shuffles need emu_launch_coop");
   const unsigned lane = emu::g_block->cur & 31u;
   return emu::shfl(v, lane ^ (unsigned)mask, true);
+}
+
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+// lanes of `mask` (all live lanes named must call) whose key equals the caller's
+static inline unsigned __match_any_sync(uint32_t mask, uint32_t key) {
+  assert(emu::g_block && "__match_any_sync needs emu_launch_coop");
+  emu::Block& B = *emu::g_block;
+  const unsigned tid = B.cur, base = tid & ~31u, w = tid >> 5, gk = (unsigned)__builtin_ctz(mask);
+  B.slot[tid] = key;
+  emu::group_barrier(w, gk, mask);
+  unsigned peers = 0;
+  for (unsigned l = 0; l < 32; l++)
+    if (((mask >> l) & 1u) && base + l < B.nthreads && !B.done[base + l] && B.slot[base + l] == key) peers |= 1u << l;
+  emu::group_barrier(w, gk, mask);
+  return peers;
+}
+static inline void __syncwarp(uint32_t mask = 0xffffffffu) {
+  assert(emu::g_block && "__syncwarp needs emu_launch_coop");
+  emu::group_barrier(emu::g_block->cur >> 5, (unsigned)__builtin_ctz(mask), mask);
+}
+static inline uint32_t __shfl_sync(uint32_t mask, uint32_t v, int src, int width = 32) {
+  assert(emu::g_block && "warp shuffles need emu_launch_coop");
+  const unsigned lane = emu::g_block->cur & 31u;
+  const unsigned seg = lane & ~((unsigned)width - 1u);
+  return emu::shfl_masked(mask, v, seg + ((unsigned)src & ((unsigned)width - 1u)));
 }
 
 // emulated launch: every thread of every block in turn; lanes in DESCENDING order inside a block, so that the
@@ -175,6 +226,7 @@ static inline void emu_launch_coop(K kernel, dim3 grid, unsigned block, A... arg
     blockIdx = dim3((unsigned)(k % grid.x), (unsigned)(k / grid.x), 0);
     B.live = block;
     B.bar_arrived = 0;
+    B.grp.clear();
     for (unsigned w = 0; w < 32; w++) { B.warp_arrived[w] = 0; B.warp_live[w] = (block > w * 32) ? std::min(32u, block - w * 32) : 0; }
     for (unsigned t = 0; t < block; t++) {
       B.done[t] = 0;

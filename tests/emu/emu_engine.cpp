@@ -30,6 +30,7 @@ struct Opts {
   int mode;           // bit 0: the real K1b scan kernels (block scans with warp shuffles) instead of a host scan
                       // bit 1: batch-affine bucket accumulation (affine_kernels.cuh, GMSM_AFFINE=1) instead of k_accumulate
                       // bit 2: every launch through the cooperative (fiber) launcher
+                      // bit 3: the lane-parallel (quad) form of the tail kernels -- carry levels, segment reduction, group sums
 };
 
 static bool g_coop_all = false;
@@ -63,9 +64,11 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
   const uint32_t n32 = (uint32_t)n;
   const size_t nbp = (size_t)p.nb_total + 1;
     // K1: digits + histogram
-    std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), entries(n * (size_t)p.nwin + 16, 0);
-    LAUNCH(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256, scalars, n32, p.c, p.nwin,
-               shared ? 0u : p.nb, digits.data(), hist.data());
+    std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), ranks(n * (size_t)p.nwin + 16, 0xFFFFFFFFu),
+        entries(n * (size_t)p.nwin + 16, 0);
+    // (warp collectives -- __match_any_sync / __shfl_sync -- inside: always the cooperative launcher)
+    emu_launch_coop(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256u, scalars, n32, p.c, p.nwin,
+                    shared ? 0u : p.nb, digits.data(), ranks.data(), hist.data());
     // K1b: exclusive scan -- the three scan kernels (cooperative launch) or a host scan
     auto scan_u32 = [&](const uint32_t* in, uint32_t* out) {
       if (o.mode & 1) { real_scan(in, (uint32_t)nbp, out); return; }
@@ -82,16 +85,30 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
         const uint32_t blo = (uint32_t)std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
         const uint32_t bhi = (uint32_t)std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
         if (blo >= bhi) continue;
-        LAUNCH(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(), n32,
-                   row_stride, hist.data(), (const uint32_t*)offsets.data(), entries.data(), blo, bhi);
+        LAUNCH(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(),
+                   (const uint32_t*)ranks.data(), n32, row_stride, (const uint32_t*)offsets.data(), entries.data(), blo, bhi);
       }
     } else {
       for (int j = 0; j < p.nwin; j++)
-        LAUNCH(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n), n32,
-                   hist.data() + (size_t)j * p.nb, (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data());
+        LAUNCH(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n),
+                   (const uint32_t*)(ranks.data() + (size_t)j * n), n32, (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data());
     }
-    for (size_t i = 0; i < nbp; i++)
-      if (hist[i] != 0) return 10;   // every counter must have been consumed exactly
+    // the ranks K1 handed out number every bucket's entries 0 .. count-1 exactly once: the scatter filled offsets[b] .. offsets[b+1]
+    // without holes or collisions iff every slot below offsets[nb_total] was written (entries start as the all-ones pattern here)
+    {
+      std::vector<uint32_t> probe(entries);
+      (void)probe;
+      std::vector<uint32_t> seen(offsets[p.nb_total], 0);
+      for (int j = 0; j < p.nwin; j++)
+        for (size_t i = 0; i < n; i++) {
+          const uint32_t code = digits[(size_t)j * n + i];
+          if (!code) continue;
+          const uint32_t b = (shared ? 0u : (uint32_t)j * p.nb) + code_bucket(code);
+          const uint32_t pos = offsets[b] + ranks[(size_t)j * n + i];
+          if (pos >= offsets[b + 1] || seen[pos]++) return 10;
+        }
+      for (uint32_t v : seen) if (v != 1) return 10;
+    }
     if (o.mode & 2) {
       // K2 (batch-affine, engine_impl.cuh's affine branch): balanced tree over the bucket-ordered entries, one shared
       // inversion per level through the hierarchical product scans
@@ -177,8 +194,12 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
         const uint32_t k2 = first ? o.K2_first : o.K2;
         first = false;
         const size_t n_out = (n_in + k2 - 1) / k2;
-        LAUNCH(k_carry_level<G>, dim3(nblk(n_out, 128)), 128, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2, buckets.data(),
-                   cp[cur ^ 1], ip[cur ^ 1]);
+        if ((o.mode & 8) && !(getenv("EMU_NOQ") && strchr(getenv("EMU_NOQ"), 'c')))
+          emu_launch_coop(k_carry_level<G, true>, dim3(nblk(n_out * 4, 128)), 128u, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2,
+                          buckets.data(), cp[cur ^ 1], ip[cur ^ 1]);
+        else
+          LAUNCH(k_carry_level<G, false>, dim3(nblk(n_out, 128)), 128, (const X*)cp[cur], (const uint32_t*)ip[cur], (uint32_t)n_in, k2, buckets.data(),
+                     cp[cur ^ 1], ip[cur ^ 1]);
         n_in = n_out;
         cur ^= 1;
       }
@@ -231,15 +252,22 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     const uint32_t L = o.L, S = (nbmax + L - 1) / L;
     const uint32_t nb_reg = shared ? p.nb_total : p.nb, nb_last = shared ? p.nb_total : p.nb_last;
     std::vector<X> seg0((size_t)red_windows * S), seg1((size_t)red_windows * ((S + 15) / 16) + 1);
-    LAUNCH(k_bucket_segments<G>, dim3(nblk((size_t)red_windows * S, 128)), 128, (const X*)buckets.data(), red_windows, nb_reg, nb_last, L, S,
-               seg0.data());
+    if ((o.mode & 8) && !(getenv("EMU_NOQ") && strchr(getenv("EMU_NOQ"), 's')))
+      emu_launch_coop(k_bucket_segments<G, true>, dim3(nblk((size_t)red_windows * S * 4, 128)), 128u, (const X*)buckets.data(), red_windows, nb_reg,
+                      nb_last, L, S, seg0.data());
+    else
+      LAUNCH(k_bucket_segments<G, false>, dim3(nblk((size_t)red_windows * S, 128)), 128, (const X*)buckets.data(), red_windows, nb_reg, nb_last, L, S,
+                 seg0.data());
     uint32_t per = S;
     X* sp[2] = {seg0.data(), seg1.data()};
     int cur = 0;
     while (per > 1) {
       const uint32_t R = 16, outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? partials.data() : sp[cur ^ 1];
-      LAUNCH(k_sum_groups<G>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
+      if ((o.mode & 8) && !(getenv("EMU_NOQ") && strchr(getenv("EMU_NOQ"), 'g')))
+        emu_launch_coop(k_sum_groups<G, true>, dim3(nblk((size_t)red_windows * outp * 4, 128)), 128u, (const X*)sp[cur], per, R, outp, red_windows, dst);
+      else
+        LAUNCH(k_sum_groups<G, false>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
       per = outp;
       cur ^= 1;
     }
@@ -252,7 +280,7 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
   // K4: finalize
   std::vector<X> scratch(red_windows);
   Jac<F> out;
-  emu_launch_coop(k_finalize<G>, dim3(1), 32u, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  emu_launch_coop(k_finalize<G>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }
@@ -266,7 +294,7 @@ int emu_finalize(const void* partials, int nranks, int c, int tables, void* out_
   const int red_windows = tables ? 1 : p.nwin;
   std::vector<X> scratch(red_windows);
   Jac<F> out;
-  emu_launch_coop(k_finalize<G>, dim3(1), 32u, (const X*)partials, nranks, red_windows, p.c, scratch.data(), &out);
+  emu_launch_coop(k_finalize<G>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials, nranks, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }

@@ -348,3 +348,30 @@ def test_emulated_sharded_window_sums_and_finalize(g, tables):
         out = np.zeros(3 * w, dtype=np.uint64)
         assert getattr(lib, "emu_finalize_%d" % k)(gathered.ctypes.data_as(vp), len(parts), c, tables, out.ctypes.data_as(vp)) == 0
         _check(g, out, want)
+
+
+@pytest.mark.parametrize("g,n", [("bn254_g1", 700), ("bls12381_g1", 260), ("bls12377_g1", 150), ("bn254_g2", 180), ("bls12381_g2", 100), ("bls12377_g2", 80)])
+def test_emulated_quad_tail(g, n):
+    """the lane-parallel (quad) form of the tail kernels (csrc/quad.cuh: one point operation per four lanes, products of a
+    formula step spread over the lanes and broadcast with masked shuffles) -- carry levels, segment reduction with its
+    double-and-add weights, group sums -- and k_finalize's quad Horner, against the oracle: cross-test ingredients
+    (infinity points, duplicates -> doubling branch, P / -P -> cancellation), plain and window-table mode, odd segment and
+    run lengths, several block orders"""
+    pts, s = make_inputs(g, n, 21)
+    want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)
+    for c, K, K2f, K2, L, tables, order in ((5, 4, 2, 3, 3, 0, 0), (8, 16, 4, 16, 32, 0, 1), (6, 7, 3, 5, 5, 1, 3)):
+        _check(g, emu_msm(g, pts, s, c, tables=tables, K=K, K2_first=K2f, K2=K2, L=L, passes=2, order=order, mode=8), want)
+
+
+def test_emulated_quad_tail_skewed_and_all_equal():
+    """quads whose chains take different branches inside one warp: all scalars equal (one bucket per window spans every chunk:
+    the carry join does all the work), all points equal (doubling branch everywhere), a single non-zero bucket"""
+    g = "bn254_g1"
+    G = O.GROUPS[g]
+    pts, s = make_inputs(g, 400, 5, specials=False)
+    s2 = s.copy()
+    s2[:] = s[0]
+    for (pp, ss) in ((pts, s2), (np.repeat(pts[:1], 400, axis=0), s), (np.repeat(pts[:1], 400, axis=0), s2)):
+        want, _, _, _ = cref.msm(g, pp, ss, c=0, nthreads=4)
+        _check(g, emu_msm(g, pp, ss, 7, K=4, K2_first=2, K2=2, L=4, mode=8), want)
+        _check(g, emu_msm(g, pp, ss, 7, K=4, K2_first=2, K2=2, L=4, mode=0), want)
