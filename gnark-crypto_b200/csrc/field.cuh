@@ -606,9 +606,9 @@ GMSM_HD Fp<P> fp_to_mont(const Fp<P>& x) {
 
 // x^-1 by Fermat (x^(q-2)); Inverse(0) = 0 like fp/element.go:1170-1172.  Any correct inversion
 // is limb-identical to the reference's Pornin GCD since the reduced Montgomery value is unique.
-// Only used once per MSM (final normalisation) and in batched-inversion kernels.
+// Kept for the batched-inversion kernels' cross-check; the engine uses fp_inv (binary GCD) below.
 template <class P>
-GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
+GMSM_HD Fp<P> fp_inv_fermat(const Fp<P>& x) {
   constexpr int N = P::N;
   // exponent e = q - 2
   uint32_t e[N];
@@ -630,6 +630,42 @@ GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
     }
   }
   return acc;
+}
+
+// x^-1 by the binary extended Euclidean algorithm on the integer a = x*R mod q (the stored limbs):
+//   invariants  x1 * a = u,  x2 * a = v  (mod q);  u, v shrink by halving / subtraction until one of them is 1.
+// <= 2 * 32N iterations of shifts and additions on N limbs -- no multiplications -- against the ~1.5 * 32N dependent
+// Montgomery products of the Fermat ladder: the inversion at the end of an MSM (FromJacobian, g1.go:150-166) sits on the
+// serial tail, where one product costs ~0.5 us of latency.  (The reference uses Pornin's optimised binary GCD,
+// fp/element.go:1173-1325; any correct inverse is limb-identical.)  a^-1 = x^-1 R^-1, so two products by R^2 bring the
+// result back to Montgomery form.  Inverse(0) = 0.  Needs one spare top bit in q (x1 + q must fit the limbs).
+template <class P>
+GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
+  constexpr int N = P::N;
+  static_assert((P::mod(N - 1) >> 31) == 0, "needs a spare top bit");
+  if (x.is_zero()) return x;
+  uint32_t u[N], v[N], x1[N], x2[N];
+  for (int i = 0; i < N; i++) { u[i] = x.l[i]; v[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
+  x1[0] = 1;
+  auto is_one = [](const uint32_t* a) { uint32_t o = a[0] ^ 1u; for (int i = 1; i < N; i++) o |= a[i]; return o == 0; };
+  auto shr1 = [](uint32_t* a) { for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[N - 1] >>= 1; };
+  auto add_mod = [](uint32_t* a) { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)a[i] + P::mod(i); a[i] = (uint32_t)c; c >>= 32; } };
+  auto geq = [](const uint32_t* a, const uint32_t* b) { for (int i = N - 1; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; } return true; };
+  auto sub = [](uint32_t* a, const uint32_t* b) { uint64_t br = 0; for (int i = 0; i < N; i++) { uint64_t d = (uint64_t)a[i] - b[i] - br; a[i] = (uint32_t)d; br = (d >> 32) & 1; } return (uint32_t)br; };
+  auto halve = [&](uint32_t* w, uint32_t* y) {   // w even: w /= 2, y /= 2 mod q
+    shr1(w);
+    if (y[0] & 1u) add_mod(y);
+    shr1(y);
+  };
+  auto sub_mod = [&](uint32_t* a, const uint32_t* b) { if (sub(a, b)) add_mod(a); };   // a = a - b mod q (a, b < q)
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1u)) halve(u, x1);
+    while (!(v[0] & 1u)) halve(v, x2);
+    if (geq(u, v)) { sub(u, v); sub_mod(x1, x2); } else { sub(v, u); sub_mod(x2, x1); }
+  }
+  Fp<P> r, r2;
+  for (int i = 0; i < N; i++) { r.l[i] = is_one(u) ? x1[i] : x2[i]; r2.l[i] = P::r2(i); }
+  return fp_mul(fp_mul(r, r2), r2);
 }
 
 // uniform coordinate-field interface (overloaded for Fp2 in fp2.cuh)

@@ -81,6 +81,12 @@ class ProvingKey:
         pts = read_slice(r, 2 * _words(CURVES[cname]), max_pk_points)
         return cls(curve, pts, device)
 
+    @classmethod
+    def from_bytes(cls, curve: str, data: bytes, n: int, raw: bool = False, check_on_curve: bool = True, device: int = 0):
+        """n G1 points in the standard encoding (Encoder.Encode of a []G1Affine without its length prefix: Bytes() each, or
+        RawBytes() each with RawEncoding, marshal.go:560-640) decoded on the device into resident bases"""
+        return cls(curve, decode_g1_points(curve, data, n, raw, check_on_curve), device)
+
     def close(self):
         self._bases.close()
 
@@ -173,3 +179,253 @@ def Commit(p: np.ndarray, pk: ProvingKey, *nbTasks: int) -> np.ndarray:
     jac = pk._bases.MultiExp(p, cfg)
     w = pk.words
     return jac[:w].copy() if jac[w:].any() else np.zeros(w, dtype=np.uint64)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# point (de)serialisation on the host -- G1Affine.RawBytes / Bytes / SetBytes (ecc/bn254/marshal.go:801-950,
+# ecc/bls12-381/marshal.go:830-1000).  Used for the few points a Fiat-Shamir transcript binds (G1Affine.Marshal is
+# RawBytes, marshal.go:779-782); bulk SRS decoding runs on the device (gmsm_g1_decode, csrc/decode.cu).
+# ----------------------------------------------------------------------------------------------------------------
+FP_MODULUS = {
+    "bn254": 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47,
+    "bls12381": 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB,
+    "bls12377": 0x01AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001,
+}
+CURVE_B = {"bn254": 3, "bls12381": 4, "bls12377": 1}     # y^2 = x^3 + b (bn254.go:12, bls12-381.go:9, bls12-377.go)
+# flag bits of the most significant byte (marshal.go:25-31 bn254: two bits; bls12-381 / bls12-377: three bits)
+_FLAGS = {
+    "bn254": dict(mask=0b11 << 6, unc=0b00 << 6, unc_inf=None, small=0b10 << 6, large=0b11 << 6, inf=0b01 << 6),
+    "bls12381": dict(mask=0b111 << 5, unc=0b000 << 5, unc_inf=0b010 << 5, small=0b100 << 5, large=0b101 << 5, inf=0b110 << 5),
+    "bls12377": dict(mask=0b111 << 5, unc=0b000 << 5, unc_inf=0b010 << 5, small=0b100 << 5, large=0b101 << 5, inf=0b110 << 5),
+}
+
+
+def _fp_words(curve: str) -> int:
+    return 4 if curve == "bn254" else 6
+
+
+def _fp_decode(limbs, curve: str) -> int:
+    L = _fp_words(curve)
+    p = FP_MODULUS[curve]
+    v = sum(int(limbs[i]) << (64 * i) for i in range(L))
+    return v * pow(1 << (64 * L), -1, p) % p
+
+
+def _fp_encode(v: int, curve: str) -> np.ndarray:
+    L = _fp_words(curve)
+    p = FP_MODULUS[curve]
+    m = (v << (64 * L)) % p
+    return np.array([(m >> (64 * i)) & (2**64 - 1) for i in range(L)], dtype=np.uint64)
+
+
+def g1_raw_bytes(point: np.ndarray, curve: str) -> bytes:
+    """G1Affine.RawBytes (marshal.go:826-846): big-endian X || Y, canonical; infinity = flag + zeroes"""
+    L = _fp_words(curve)
+    point = np.ascontiguousarray(point, dtype=np.uint64).reshape(2 * L)
+    nb = 8 * L
+    if not point.any():
+        f = _FLAGS[curve]
+        out = bytearray(2 * nb)
+        out[0] = f["unc"] if f["unc_inf"] is None else f["unc_inf"]
+        return bytes(out)
+    x, y = _fp_decode(point[:L], curve), _fp_decode(point[L:], curve)
+    return x.to_bytes(nb, "big") + y.to_bytes(nb, "big")      # mUncompressed = 0: no bits to set
+
+
+def g1_bytes(point: np.ndarray, curve: str) -> bytes:
+    """G1Affine.Bytes (marshal.go:801-823): compressed -- big-endian X with the flag bits in the top byte"""
+    L = _fp_words(curve)
+    point = np.ascontiguousarray(point, dtype=np.uint64).reshape(2 * L)
+    nb = 8 * L
+    f = _FLAGS[curve]
+    if not point.any():
+        out = bytearray(nb)
+        out[0] = f["inf"]
+        return bytes(out)
+    p = FP_MODULUS[curve]
+    x, y = _fp_decode(point[:L], curve), _fp_decode(point[L:], curve)
+    out = bytearray(x.to_bytes(nb, "big"))
+    out[0] |= f["large"] if y > (p - 1) // 2 else f["small"]        # LexicographicallyLargest, fp/element.go:282-296
+    return bytes(out)
+
+
+def g1_set_bytes(buf: bytes, curve: str):
+    """G1Affine.SetBytes without the subgroup check (marshal.go:858-950) for ONE point on the host -> (point limbs, consumed).
+    Raises ValueError with the reference's messages on invalid encodings."""
+    L = _fp_words(curve)
+    nb = 8 * L
+    f = _FLAGS[curve]
+    p = FP_MODULUS[curve]
+    if len(buf) < nb:
+        raise EOFError("short buffer")
+    m = buf[0] & f["mask"]
+    if m == f["inf"]:
+        if (buf[0] & ~f["mask"] & 0xFF) or any(buf[1:nb]):
+            raise ValueError("invalid infinity point encoding")
+        return np.zeros(2 * L, dtype=np.uint64), nb
+    if f["unc_inf"] is not None and m == f["unc_inf"]:
+        if len(buf) < 2 * nb:
+            raise EOFError("short buffer")
+        if (buf[0] & ~f["mask"] & 0xFF) or any(buf[1:2 * nb]):
+            raise ValueError("invalid infinity point encoding")
+        return np.zeros(2 * L, dtype=np.uint64), 2 * nb
+    xb = bytearray(buf[:nb])
+    xb[0] &= ~f["mask"] & 0xFF
+    x = int.from_bytes(xb, "big")
+    if x >= p:
+        raise ValueError("invalid fp.Element encoding")
+    if m == f["unc"]:
+        if len(buf) < 2 * nb:
+            raise EOFError("short buffer")
+        y = int.from_bytes(buf[nb:2 * nb], "big")
+        if y >= p:
+            raise ValueError("invalid fp.Element encoding")
+        return np.concatenate([_fp_encode(x, curve), _fp_encode(y, curve)]), 2 * nb
+    if m not in (f["small"], f["large"]):
+        raise ValueError("invalid point encoding")
+    y2 = (x * x * x + CURVE_B[curve]) % p
+    if p % 4 == 3:
+        y = pow(y2, (p + 1) // 4, p)
+    else:                                   # Tonelli-Shanks (bls12-377: q = 1 mod 4, fp/element.go Sqrt)
+        y = _tonelli(y2, p)
+    if y is None or y * y % p != y2:
+        raise ValueError("invalid compressed coordinate: square root doesn't exist")
+    if (y > (p - 1) // 2) != (m == f["large"]):
+        y = p - y
+    return np.concatenate([_fp_encode(x, curve), _fp_encode(y, curve)]), nb
+
+
+def _tonelli(a: int, p: int):
+    if a == 0:
+        return 0
+    if pow(a, (p - 1) // 2, p) != 1:
+        return None
+    q, s = p - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    z = 2
+    while pow(z, (p - 1) // 2, p) != p - 1:
+        z += 1
+    m, c, t, r = s, pow(z, q, p), pow(a, q, p), pow(a, (q + 1) // 2, p)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % p
+            i += 1
+        b = pow(c, 1 << (m - i - 1), p)
+        m, c, t, r = i, b * b % p, t * b * b % p, r * b % p
+    return r
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batched openings at one point (kzg.go:246-420): the prover side; verification (pairings) is out of scope
+# ----------------------------------------------------------------------------------------------------------------
+class ErrInvalidNbDigests(MultiExpError):
+    """kzg.ErrInvalidNbDigests (kzg.go:23)"""
+
+
+@dataclass
+class BatchOpeningProof:
+    """kzg.BatchOpeningProof{H G1Affine, ClaimedValues []fr.Element} (kzg.go:66-77)"""
+
+    H: np.ndarray
+    ClaimedValues: np.ndarray
+
+
+def _fr_marshal(limbs, r: int) -> bytes:
+    """fr.Element.Marshal (fr/element.go:868-871): 32 bytes big-endian, canonical value"""
+    return _fr_decode(np.asarray(limbs, dtype=np.uint64), r)[0].to_bytes(32, "big")
+
+
+def derive_gamma(point, digests, claimed_values, hf, curve: str, *data_transcript: bytes) -> int:
+    """deriveGamma (kzg.go:531-563) over fiatshamir.Transcript (fiat-shamir/transcript.go:61-131) with the single challenge
+    "gamma": H("gamma" || point || digests (RawBytes) || claimed values || extra data), read big-endian and reduced mod r
+    (fr.SetBytes, fr/element.go:880-903).  `hf` is a hashlib constructor (e.g. hashlib.sha256)."""
+    c = curve.split("_")[0]
+    r = FR_MODULUS[c]
+    h = hf()
+    h.update(b"gamma")
+    h.update(_fr_marshal(point, r))
+    for d in digests:
+        h.update(g1_raw_bytes(d, c))
+    for v in np.ascontiguousarray(claimed_values, dtype=np.uint64).reshape(-1, 4):
+        h.update(_fr_marshal(v, r))
+    for b in data_transcript:
+        h.update(b)
+    return int.from_bytes(h.digest(), "big") % r
+
+
+def BatchOpenSinglePoint(polynomials, digests, point: np.ndarray, hf, pk: ProvingKey, *data_transcript: bytes) -> BatchOpeningProof:
+    """kzg.BatchOpenSinglePoint (kzg.go:246-331): ClaimedValues[i] = f_i(point); gamma by Fiat-Shamir; the folded polynomial
+    sum_i gamma^i f_i is divided by (X - point) on the host (Fr loops, as in the reference) and committed with ONE MultiExp
+    over the resident bases."""
+    if len(digests) != len(polynomials):
+        raise ErrInvalidNbDigests("number of digests is not the same as the number of polynomials")
+    c = pk.curve.split("_")[0]
+    r = FR_MODULUS[c]
+    polys = []
+    for p in polynomials:
+        p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4)
+        if p.shape[0] == 0 or p.shape[0] > pk.G1.shape[0]:
+            raise ErrInvalidPolynomialSize("invalid polynomial size (larger than SRS or == 0)")
+        polys.append(_fr_decode(p, r))
+    a = _fr_decode(point, r)[0]
+    claimed = [_eval(f, a, r) for f in polys]
+    claimed_limbs = _fr_encode(claimed, r)
+    gamma = derive_gamma(point, digests, claimed_limbs, hf, c, *data_transcript)
+    folded_eval = claimed[-1]
+    for v in reversed(claimed[:-1]):
+        folded_eval = (folded_eval * gamma + v) % r
+    largest = max(len(f) for f in polys)
+    folded = list(polys[0]) + [0] * (largest - len(polys[0]))
+    g = 1
+    for f in polys[1:]:
+        g = g * gamma % r
+        for j, v in enumerate(f):
+            folded[j] = (folded[j] + v * g) % r
+    h = _divide_by_x_minus_a(folded, folded_eval, a, r)
+    if not h:
+        raise ErrInvalidPolynomialSize("invalid polynomial size (larger than SRS or == 0)")
+    H = Commit(_fr_encode(h, r), pk)
+    return BatchOpeningProof(H=H.reshape(pk.words), ClaimedValues=claimed_limbs)
+
+
+def FoldProof(digests, proof: BatchOpeningProof, point: np.ndarray, hf, curve: str, *data_transcript: bytes):
+    """kzg.FoldProof (kzg.go:341-380) -> (OpeningProof, folded digest): the claimed values are folded with [1, gamma, ...] on the
+    host, the digests with one MultiExp (`fold`, kzg.go:506-528 -- the reference calls MultiExp for it too)."""
+    from .multiexp import curve_package
+
+    claimed = np.ascontiguousarray(proof.ClaimedValues, dtype=np.uint64).reshape(-1, 4)
+    if len(digests) != claimed.shape[0]:
+        raise ErrInvalidNbDigests("number of digests is not the same as the number of polynomials")
+    c = curve.split("_")[0]
+    r = FR_MODULUS[c]
+    gamma = derive_gamma(point, digests, claimed, hf, c, *data_transcript)
+    gam = [1]
+    for _ in range(1, len(digests)):
+        gam.append(gam[-1] * gamma % r)
+    vals = _fr_decode(claimed, r)
+    folded_eval = sum(v * g for v, g in zip(vals, gam)) % r
+    aff_cls = curve_package(c)[0]
+    pts = np.ascontiguousarray(np.stack([np.asarray(d, dtype=np.uint64).reshape(-1) for d in digests]))
+    folded_digest = aff_cls().MultiExp(pts, _fr_encode(gam, r), MultiExpConfig()).limbs
+    return OpeningProof(H=np.array(proof.H, dtype=np.uint64), ClaimedValue=_fr_encode([folded_eval], r)[0]), folded_digest
+
+
+def decode_g1_points(curve: str, data: bytes, n: int, raw: bool = False, check_on_curve: bool = True) -> np.ndarray:
+    """bulk G1Affine.SetBytes on the GPU (gmsm_g1_decode, csrc/decode.cu): n points of a homogeneous stream -> (n, words) uint64
+    in Go memory layout.  Raises MultiExpError with the reference's message and the index of the first invalid point."""
+    from . import _native
+
+    cname = curve + "_g1" if not curve.endswith("_g1") else curve
+    words = 2 * _words(CURVES[cname])
+    per = 8 * words if raw else 4 * words
+    if len(data) < n * per:
+        raise EOFError("short buffer")      # io.ErrShortBuffer
+    buf = np.frombuffer(data, dtype=np.uint8, count=n * per)
+    out = np.zeros((n, words), dtype=np.uint64)
+    rc = _native.lib().gmsm_g1_decode(CURVES[cname], buf.ctypes.data, n, 1 if raw else 0, 1 if check_on_curve else 0, out.ctypes.data)
+    if rc != 0:
+        raise MultiExpError(_native.last_error())
+    return out
