@@ -230,18 +230,18 @@ def run_reference(args, rank, world):
     cores = ncores()
     logn_total = args.total_logn if args.total_logn else (args.logn if world == 1 else 26)
     base = G.encode_affine([G.scalar_mul(G.gen, BASE_MULT)])[0]
-    # probe: one 2^18 step decides the per-step size
-    probe_log = min(18, logn_total)
+    # probe: one 2^20 step decides the per-step size (full size unless K + W steps of it would exceed the budget)
+    probe_log = min(20, logn_total)
     pts = cref.generate_multiples(g, base, 1, 1 << probe_log, nthreads=cores)
     s = synth_scalars(1 << probe_log, CURVE_BITS[g], 0x5EED0000 + 2)
     cref.msm(g, pts, s, c=0, nthreads=cores)
     t0 = time.perf_counter()
     cref.msm(g, pts, s, c=0, nthreads=cores)
     probe_rate = (1 << probe_log) / (time.perf_counter() - t0)
-    budget_s = float(os.environ.get("GMSM_REF_BUDGET_S", "150"))
+    budget_s = float(os.environ.get("GMSM_REF_BUDGET_S", "300"))
     logs = args.sample_logn if args.sample_logn else logn_total
-    while not args.sample_logn and logs > 16 and (args.steps + args.warmup) * (1 << logs) / (1.5 * probe_rate) > budget_s:
-        logs -= 1          # (large MSMs run ~1.5x the probe's rate per point)
+    while not args.sample_logn and logs > 16 and (args.steps + args.warmup) * (1 << logs) / probe_rate > budget_s:
+        logs -= 1
     n = 1 << logs
     if n != (1 << probe_log):
         pts = cref.generate_multiples(g, base, 1, n, nthreads=cores)

@@ -49,11 +49,12 @@ struct gmsm_ctx {
   uint32_t K2_first = 4;    // items per thread of the first carry level (GMSM_K2_FIRST): 4x the threads for the level that
                             // holds nearly all the carry additions (measured 0.87 -> 0.73 ms at bn254 G1 2^24)
   uint32_t seg_L = 32, seg_S = 0;
-  // lane-parallel tail (quad.cuh): a stage with `items` independent chains runs one QUAD of lanes per chain when four
-  // times the threads still fit the machine in about one wave (latency-bound regime); GMSM_QUAD=0 / 1 forces it off / on
-  int quad_mode = -1;
-  size_t quad_max_items = 148 * 512;
-  bool use_quad(size_t items) const { return quad_mode < 0 ? items <= quad_max_items : quad_mode != 0; }
+  // lane-parallel tail (quad.cuh): one QUAD of lanes per chain instead of one thread.  Measured slower than the serial form
+  // on B200 for every group and size (profiles/r02_ab_quad_tail_call2.txt), so it is OFF unless GMSM_QUAD=1 asks for it
+  // (GMSM_QUAD_MAX then bounds the number of chains a stage may have to use it).
+  int quad_mode = 0;
+  size_t quad_max_items = (size_t)1 << 40;
+  bool use_quad(size_t items) const { return quad_mode > 0 && items <= quad_max_items; }
   // device workspace
   uint32_t* hist = nullptr;      // nb_total + 1 (+pad)
   uint32_t* offsets = nullptr;   // nb_total + 1

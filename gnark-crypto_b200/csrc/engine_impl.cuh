@@ -254,15 +254,15 @@ static int run_bucket_reduce(gmsm_ctx* c, void* d_partials, cudaStream_t st) {
     uint32_t per = S;
     int cur = 0;
     while (per > 1) {
-      uint32_t R = 16;
+      const bool quad = c->use_quad((size_t)nwin * per);
+      const uint32_t R = quad ? 16u : 2u * TREE_THREADS;
       uint32_t outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? reinterpret_cast<X*>(d_partials) : reinterpret_cast<X*>(c->seg[cur ^ 1]);
-      if (c->use_quad((size_t)nwin * outp))
+      if (quad)
         k_sum_groups<G, true><<<nblk((size_t)nwin * outp * 4, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
                                                                              nwin, dst);
       else
-        k_sum_groups<G, false><<<nblk((size_t)nwin * outp, 128), 128, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, R, outp,
-                                                                          nwin, dst);
+        k_sum_tree<G><<<dim3(outp, (unsigned)nwin), TREE_THREADS, 0, st>>>(reinterpret_cast<const X*>(c->seg[cur]), per, outp, dst);
       launches++;
       LAUNCH_CHECK();
       per = outp;
@@ -288,8 +288,12 @@ static int run_window_sums(gmsm_ctx* c, const void* d_points, const void* d_scal
 template <class G>
 static int run_finalize(gmsm_ctx* c, const void* d_partials, int nranks, void* d_out, cudaStream_t st) {
   using F = typename G::F;
-  k_finalize<G><<<1, FIN_THREADS, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
-                                  reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
+  if (c->quad_mode > 0)
+    k_finalize<G, true><<<1, FIN_THREADS, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
+                                                   reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
+  else
+    k_finalize<G, false><<<1, FIN_THREADS, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_partials), nranks, c->red_windows(), c->plan.c,
+                                                    reinterpret_cast<XYZZ<F>*>(c->fin_scratch), reinterpret_cast<Jac<F>*>(d_out));
   LAUNCH_CHECK();
   return GMSM_OK;
 }

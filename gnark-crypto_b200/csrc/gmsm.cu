@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -437,65 +438,74 @@ class CopyPool {
     static CopyPool* p = new CopyPool();   // leaked on purpose: worker threads must not be joined from a static destructor
     return *p;
   }
-  // dst[0..n) = src[0..n), split over the pool; blocks until done.  One job at a time (the phases are bandwidth-bound).
+  // dst[0..n) = src[0..n), cut into 1 MiB parts on a queue shared by all callers; the caller works on the queue too and
+  // returns when ITS parts are done.  Concurrent calls (several MultiExp at once) interleave their parts.
   void copy(char* dst, const char* src, size_t n) {
     if (nthreads_ <= 1 || n < (size_t)(2 << 20)) { memcpy(dst, src, n); return; }
-    std::lock_guard<std::mutex> run(run_mu_);
+    Job job;
+    job.remaining.store((int)((n + PART - 1) / PART));
     {
       std::lock_guard<std::mutex> lk(mu_);
-      d_ = dst; s_ = src; n_ = n;
-      parts_ = (int)((n + PART - 1) / PART);
-      next_.store(0);
-      remaining_.store(parts_);
-      gen_++;
+      for (size_t off = 0; off < n; off += PART) q_.push_back(Part{dst + off, src + off, std::min(PART, n - off), &job});
     }
     cv_work_.notify_all();
-    work();   // the caller takes parts too
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return remaining_.load() == 0; });
+    for (;;) {
+      Part p;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (q_.empty()) break;
+        p = q_.front();
+        q_.pop_front();
+      }
+      run(p);
+    }
+    std::unique_lock<std::mutex> lk(job.mu);
+    job.cv.wait(lk, [&] { return job.remaining.load() == 0; });
   }
   int threads() const { return nthreads_; }
 
  private:
   static constexpr size_t PART = 1 << 20;
+  struct Job {
+    std::atomic<int> remaining{0};
+    std::mutex mu;
+    std::condition_variable cv;
+  };
+  struct Part {
+    char* d;
+    const char* s;
+    size_t n;
+    Job* job;
+  };
   CopyPool() {
     int hw = (int)std::thread::hardware_concurrency();
-    nthreads_ = std::max(1, std::min(8, hw / 4));
+    nthreads_ = std::max(1, std::min(16, hw / 4));
     if (const char* e = getenv("GMSM_COPY_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nthreads_ = v; }
     for (int i = 1; i < nthreads_; i++) std::thread([this] { loop(); }).detach();
   }
-  void work() {
-    for (;;) {
-      const int k = next_.fetch_add(1);
-      if (k >= parts_) return;
-      const size_t off = (size_t)k * PART, len = std::min(PART, n_ - off);
-      memcpy(d_ + off, s_ + off, len);
-      if (remaining_.fetch_sub(1) == 1) {
-        std::lock_guard<std::mutex> lk(mu_);
-        cv_done_.notify_all();
-      }
+  static void run(const Part& p) {
+    memcpy(p.d, p.s, p.n);
+    if (p.job->remaining.fetch_sub(1) == 1) {
+      std::lock_guard<std::mutex> lk(p.job->mu);   // (the waiter holds job.mu while it checks: no lost wake-up, no use after free)
+      p.job->cv.notify_all();
     }
   }
   void loop() {
-    uint64_t seen = 0;
     for (;;) {
+      Part p;
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_work_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
+        cv_work_.wait(lk, [&] { return !q_.empty(); });
+        p = q_.front();
+        q_.pop_front();
       }
-      work();
+      run(p);
     }
   }
   int nthreads_ = 1;
-  std::mutex run_mu_, mu_;
-  std::condition_variable cv_work_, cv_done_;
-  uint64_t gen_ = 0;
-  char* d_ = nullptr;
-  const char* s_ = nullptr;
-  size_t n_ = 0;
-  int parts_ = 0;
-  std::atomic<int> next_{0}, remaining_{0};
+  std::mutex mu_;
+  std::condition_variable cv_work_;
+  std::deque<Part> q_;
 };
 
 struct Stager {

@@ -120,46 +120,53 @@ GMSM_D XYZZ<F> tail_double(const Quad& q, const XYZZ<F>& a) {
 // Semantics of partitionScalars (multiexp.go:743-800): zero scalars skipped; digit = carry + c bits;
 // windows 0..W-2 borrow (digit > 2^(c-1)-1 -> digit -= 2^c, carry 1); last window never borrows.
 // ------------------------------------------------------------------------------------------
-// SHORTCUT = false drops the early exit for zero scalars (they then walk the loop and produce the same all-zero digits):
-// callers that use warp-collective operations inside fn need every lane in the same iteration.
-template <class G, bool SHORTCUT = true, class Fn>
-GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn) {
-  using Fr = typename G::Fr;
-  constexpr int N = Fr::N;
-  if (SHORTCUT && s_mont.is_zero()) {     // IsZero() on the Montgomery limbs, multiexp.go:743
-    for (int j = 0; j < nwin; j++) fn(j, 0u);
-    return;
-  }
-  Fr k = fp_from_mont(s_mont);            // Bits(), fr/element.go:855-859
+// One scalar's signed digits, window by window (next() must be called for j = 0, 1, ..., W-1 in order).
+template <class G>
+struct DigitStream {
+  static constexpr int N = G::Fr::N;
   uint32_t v[N];
+  uint32_t carry, mask, maxd;
+  int c, nwin;
+  GMSM_D void init(const typename G::Fr& s_mont, int c_, int nwin_) {
+    const typename G::Fr k = fp_from_mont(s_mont);            // Bits(), fr/element.go:855-859
 #pragma unroll
-  for (int i = 0; i < N; i++) v[i] = k.l[i];
-  const uint32_t mask = (1u << c) - 1u;
-  const uint32_t maxd = (1u << (c - 1)) - 1u;
-  uint32_t carry = 0;
-  for (int j = 0; j < nwin; j++) {
+    for (int i = 0; i < N; i++) v[i] = k.l[i];
+    c = c_;
+    nwin = nwin_;
+    mask = (1u << c_) - 1u;
+    maxd = (1u << (c_ - 1)) - 1u;
+    carry = 0;
+  }
+  GMSM_D uint32_t next(int j) {
     uint32_t d = (v[0] & mask) + carry;
     // 256-bit logical shift right by c (c < 32)
 #pragma unroll
     for (int i = 0; i < N - 1; i++) v[i] = __funnelshift_r(v[i], v[i + 1], c);
     v[N - 1] >>= c;
-    uint32_t code;
     if (j < nwin - 1) {
       carry = 0;
       if (d > maxd) {
         // negative digit d - 2^c, magnitude 2^c - d  (0 when an all-ones window meets a carry:
         // digit 0 with a carry out, nothing to add)
-        uint32_t mag = (1u << c) - d;
+        const uint32_t mag = (1u << c) - d;
         carry = 1;
-        code = mag ? (((mag - 1u) << 1) | 1u) : 0u;
-      } else {
-        code = d << 1;
+        return mag ? (((mag - 1u) << 1) | 1u) : 0u;
       }
-    } else {
-      code = d << 1;  // multiexp.go:788-800: the last window never borrows
+      return d << 1;
     }
-    fn(j, code);
+    return d << 1;  // multiexp.go:788-800: the last window never borrows
   }
+};
+
+template <class G, class Fn>
+GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn) {
+  if (s_mont.is_zero()) {                 // IsZero() on the Montgomery limbs, multiexp.go:743
+    for (int j = 0; j < nwin; j++) fn(j, 0u);
+    return;
+  }
+  DigitStream<G> ds;
+  ds.init(s_mont, c, nwin);
+  for (int j = 0; j < nwin; j++) fn(j, ds.next(j));
 }
 
 // bucket index inside its window for a non-zero code: magnitude - 1
@@ -173,29 +180,52 @@ GMSM_D uint32_t code_bucket(uint32_t code) { return (code >> 1) - 1u + (code & 1
 // otherwise put millions of atomics on a handful of addresses; here all W hot addresses of such an input are in flight at
 // once (one kernel for all windows) instead of one per scatter launch.
 // The loop is block-uniform and lanes past the end walk it with a zero scalar: every lane of a warp reaches the collectives.
+// The returning atomics of DIGIT_BATCH windows are issued back to back and consumed afterwards, so a thread waits for one
+// L2 round trip per batch instead of one per window (measured: 3.9 ms -> see DESIGN.md for n = 2^24, W = 15 with one
+// dependent round trip per window).
+static constexpr int DIGIT_BATCH = 8;
 template <class G>
 __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
                               uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ ranks, uint32_t* __restrict__ hist) {
   using Fr = typename G::Fr;
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i64 = base + threadIdx.x;
     const bool valid = i64 < n;
     const uint32_t i = (uint32_t)i64;
     Fr s = Fr::zero();
     if (valid) s = load_vec_ro(scalars + i);
-    for_each_digit<G, false>(s, c, nwin, [&](int j, uint32_t code) {
-      const uint32_t key = code ? (uint32_t)j * nb + code_bucket(code) : ID_NONE;
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      if (code) {
-        const int leader = __ffs((int)peers) - 1;
-        uint32_t first = 0;
-        if ((int)lane == leader) first = atomicAdd(&hist[key], (uint32_t)__popc(peers));
-        first = __shfl_sync(peers, first, leader);
-        ranks[(size_t)j * n + i] = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    DigitStream<G> ds;
+    ds.init(s, c, nwin);       // (a zero scalar walks the windows like any other: all its digits are 0, multiexp.go:743)
+    for (int j0 = 0; j0 < nwin; j0 += DIGIT_BATCH) {
+      uint32_t code[DIGIT_BATCH], first[DIGIT_BATCH];
+      unsigned peers[DIGIT_BATCH];
+#pragma unroll
+      for (int b = 0; b < DIGIT_BATCH; b++) {
+        const int j = j0 + b;
+        code[b] = 0;
+        peers[b] = 0;
+        first[b] = 0;
+        if (j < nwin) {                                  // warp-uniform
+          code[b] = ds.next(j);
+          const uint32_t key = code[b] ? (uint32_t)j * nb + code_bucket(code[b]) : ID_NONE;
+          peers[b] = __match_any_sync(0xffffffffu, key);
+          if (code[b] && (int)lane == __ffs((int)peers[b]) - 1) first[b] = atomicAdd(&hist[key], (uint32_t)__popc(peers[b]));
+        }
       }
-      if (valid) digits[(size_t)j * n + i] = code;
-    });
+#pragma unroll
+      for (int b = 0; b < DIGIT_BATCH; b++) {
+        const int j = j0 + b;
+        if (j < nwin) {
+          if (code[b]) {
+            const uint32_t f = __shfl_sync(peers[b], first[b], __ffs((int)peers[b]) - 1);
+            ranks[(size_t)j * n + i] = f + (uint32_t)__popc(peers[b] & lt);
+          }
+          if (valid) digits[(size_t)j * n + i] = code[b];
+        }
+      }
+    }
   }
 }
 
@@ -597,43 +627,87 @@ k_sum_groups(const XYZZ<typename G::F>* __restrict__ in, uint32_t in_per_win, ui
   if (!Q || qd.ql == 0) store_vec(out + (size_t)j * out_per_win + g, acc);
 }
 
+// out[j][g] = sum of in[j][128 g .. 128 g + 128): a block-level binary tree (each thread adds two inputs, then six
+// shared-memory levels), so a launch shortens every window's list 128-fold along a chain of only 7 additions -- the
+// group sums above walk 16 additions per 16-fold level (48 for 2048 segment results, against 14 here).
+static constexpr int TREE_THREADS = 64;
+template <class G>
+__global__ void __launch_bounds__(TREE_THREADS)
+k_sum_tree(const XYZZ<typename G::F>* __restrict__ in, uint32_t in_per_win, uint32_t out_per_win, XYZZ<typename G::F>* __restrict__ out) {
+  using F = typename G::F;
+  __shared__ XYZZ<F> sm[TREE_THREADS];
+  const uint32_t j = blockIdx.y, g = blockIdx.x, t = threadIdx.x;
+  const uint32_t base = g * 2u * TREE_THREADS;
+  const XYZZ<F>* src = in + (size_t)j * in_per_win;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (base + t < in_per_win) acc = load_vec(src + base + t);
+  if (base + t + TREE_THREADS < in_per_win) {
+    XYZZ<F> q = load_vec(src + base + t + TREE_THREADS);
+    xyzz_add_cold(acc, q);
+  }
+  for (uint32_t s = TREE_THREADS / 2; s >= 1; s >>= 1) {
+    store_vec(&sm[t], acc);
+    __syncthreads();
+    if (t < s) {
+      XYZZ<F> q = load_vec(&sm[t + s]);
+      xyzz_add_cold(acc, q);
+    }
+    __syncthreads();
+  }
+  if (t == 0) store_vec(out + (size_t)j * out_per_win + g, acc);
+}
+
 // ------------------------------------------------------------------------------------------
-// K4: finalize (one block of FIN_THREADS).  partials[r][j], r < nranks, j < nwin.  Quads sum over the ranks, window-parallel;
-// then quad 0 runs the Horner chain -- c * (W - 1) dependent doublings, the longest serial chain of an MSM -- with the
-// lane-parallel formulas of quad.cuh (three product steps per doubling instead of seven).
+// K4: finalize (one block of FIN_THREADS).  partials[r][j], r < nranks, j < nwin.  Lanes sum over the ranks, window-parallel;
+// then ONE thread runs the Horner chain -- c * (W - 1) dependent doublings, the longest serial chain of an MSM.  Q = true is
+// the lane-parallel form (quad.cuh: three product steps per doubling instead of seven); it measured SLOWER on B200
+// (profiles/r02_ab_quad_tail_call2.txt: a lone warp is bound by the ~5 cycles per dependent instruction, and the operand
+// selects and shuffles of a lane-parallel step cost as many instructions as they save) and is kept behind GMSM_QUAD=1.
 // ------------------------------------------------------------------------------------------
 static constexpr int FIN_THREADS = 64;
 template <class F>
 __device__ __noinline__ Jac<F> jac_double_quad_cold(Quad q, const Jac<F>& p) {
   return jac_double_quad(q, p);
 }
-template <class G>
+template <class F>
+__device__ __noinline__ Jac<F> jac_double_cold1(const Jac<F>& p) {
+  return jac_double(p);
+}
+template <class G, bool Q>
 __global__ void __launch_bounds__(FIN_THREADS)
 k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int nranks, int nwin, int c,
            XYZZ<typename G::F>* __restrict__ scratch /* nwin */, Jac<typename G::F>* __restrict__ out) {
   using F = typename G::F;
   const Quad qd = quad_of_thread();
-  for (int j = threadIdx.x >> 2; j < nwin; j += blockDim.x >> 2) {
+  // sum over the ranks, window-parallel (one lane -- or one quad -- per window)
+  const int stride = Q ? (int)(blockDim.x >> 2) : (int)blockDim.x;
+  for (int j = Q ? (int)(threadIdx.x >> 2) : (int)threadIdx.x; j < nwin; j += stride) {
     XYZZ<F> acc = load_vec(partials + j);
     for (int r = 1; r < nranks; r++) {
       XYZZ<F> q = load_vec(partials + (size_t)r * nwin + j);
-      xyzz_add_quad_cold(qd, acc, q);
+      tail_add<Q>(qd, acc, q);
     }
-    if (qd.ql == 0) store_vec(scratch + j, acc);
+    if (!Q || qd.ql == 0) store_vec(scratch + j, acc);
   }
   __syncthreads();
-  if (threadIdx.x >= 4) return;
+  if (threadIdx.x >= (Q ? 4u : 1u)) return;
   // Horner over the windows, high -> low: acc = 2^c * acc + T_j.  The c doublings run in Jacobian
   // coordinates (2M + 5S each instead of 6M + 3S); the addition of T_j in extended Jacobian.
   XYZZ<F> acc = load_vec(scratch + (nwin - 1));
   for (int j = nwin - 2; j >= 0; j--) {
-    Jac<F> dj = xyzz_to_jac_quad(qd, acc);
-    for (int l = 0; l < c; l++) dj = jac_double_quad_cold(qd, dj);
-    acc = jac_to_xyzz_quad(qd, dj);
+    if constexpr (Q) {
+      Jac<F> dj = xyzz_to_jac_quad(qd, acc);
+      for (int l = 0; l < c; l++) dj = jac_double_quad_cold(qd, dj);
+      acc = jac_to_xyzz_quad(qd, dj);
+    } else {
+      Jac<F> dj = xyzz_to_jac(acc);
+      for (int l = 0; l < c; l++) dj = jac_double_cold1(dj);
+      acc = jac_to_xyzz(dj);
+    }
     XYZZ<F> q = load_vec(scratch + j);
-    xyzz_add_quad_cold(qd, acc, q);
+    tail_add<Q>(qd, acc, q);
   }
-  Jac<F> jac = xyzz_to_jac_quad(qd, acc);
+  Jac<F> jac = xyzz_to_jac(acc);
   Affine<F> a = jac_to_affine(jac);
   Jac<F> o;
   if (jac.z.is_zero()) {
@@ -641,7 +715,7 @@ k_finalize(const XYZZ<typename G::F>* __restrict__ partials, int nranks, int nwi
   } else {
     o = Jac<F>{a.x, a.y, F::one()};
   }
-  if (qd.ql == 0) store_vec(out, o);
+  if (!Q || qd.ql == 0) store_vec(out, o);
 }
 
 // ------------------------------------------------------------------------------------------

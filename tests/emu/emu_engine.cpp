@@ -262,12 +262,13 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
     X* sp[2] = {seg0.data(), seg1.data()};
     int cur = 0;
     while (per > 1) {
-      const uint32_t R = 16, outp = (per + R - 1) / R;
+      const bool quad = (o.mode & 8) && !(getenv("EMU_NOQ") && strchr(getenv("EMU_NOQ"), 'g'));
+      const uint32_t R = quad ? 16u : 2u * TREE_THREADS, outp = (per + R - 1) / R;
       X* dst = (outp == 1) ? partials.data() : sp[cur ^ 1];
-      if ((o.mode & 8) && !(getenv("EMU_NOQ") && strchr(getenv("EMU_NOQ"), 'g')))
+      if (quad)
         emu_launch_coop(k_sum_groups<G, true>, dim3(nblk((size_t)red_windows * outp * 4, 128)), 128u, (const X*)sp[cur], per, R, outp, red_windows, dst);
-      else
-        LAUNCH(k_sum_groups<G, false>, dim3(nblk((size_t)red_windows * outp, 128)), 128, (const X*)sp[cur], per, R, outp, red_windows, dst);
+      else     // block tree with barriers: cooperative launcher
+        emu_launch_coop(k_sum_tree<G>, dim3(outp, (unsigned)red_windows), (unsigned)TREE_THREADS, (const X*)sp[cur], per, outp, dst);
       per = outp;
       cur ^= 1;
     }
@@ -280,7 +281,8 @@ int emu_msm(const void* points_v, const void* scalars_v, size_t n, const Opts& o
   // K4: finalize
   std::vector<X> scratch(red_windows);
   Jac<F> out;
-  emu_launch_coop(k_finalize<G>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  if (o.mode & 8) emu_launch_coop(k_finalize<G, true>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
+  else emu_launch_coop(k_finalize<G, false>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials.data(), 1, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }
@@ -294,7 +296,7 @@ int emu_finalize(const void* partials, int nranks, int c, int tables, void* out_
   const int red_windows = tables ? 1 : p.nwin;
   std::vector<X> scratch(red_windows);
   Jac<F> out;
-  emu_launch_coop(k_finalize<G>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials, nranks, red_windows, p.c, scratch.data(), &out);
+  emu_launch_coop(k_finalize<G, false>, dim3(1), (unsigned)FIN_THREADS, (const X*)partials, nranks, red_windows, p.c, scratch.data(), &out);
   std::memcpy(out_jac, &out, sizeof(out));
   return 0;
 }
