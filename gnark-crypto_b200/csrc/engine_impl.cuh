@@ -38,7 +38,9 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->ranks, c->hist);
+    k_skew_probe<G><<<1, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->hist + nbp + 4);    // flag lives in the pad of hist[] (just cleared)
+    k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->ranks, c->hist, c->hist + nbp + 4);
+    launches++;
     launches++;
     LAUNCH_CHECK();
   }

@@ -429,7 +429,7 @@ extern "C" int gmsm_ctx_msm_tables_device(gmsm_ctx_t* ctx, const void* d_table, 
 // A Go caller hands over ordinary (pageable) slices (cgo pins them only for the duration of the call and
 // the library must not keep them).  cudaMemcpyAsync from pageable memory is staged by the driver through one bounce buffer,
 // synchronously on the calling thread, at a fraction of the PCIe rate.  The library therefore stages such buffers itself:
-// a few host threads copy 8 MiB pieces into a ring of pinned slots, each slot is sent with a true asynchronous H2D copy as
+// a few host threads copy 32 MiB pieces (in 2 MiB parts) into a ring of pinned slots, each slot is sent with a true asynchronous H2D copy as
 // soon as it is full, and the calling thread moves on to fill the next slot -- memcpy, PCIe and the GPU's bucket pass of
 // the previous batch all overlap.  Buffers that are already pinned / registered (cudaPointerGetAttributes) skip the ring.
 class CopyPool {
@@ -465,7 +465,7 @@ class CopyPool {
   int threads() const { return nthreads_; }
 
  private:
-  static constexpr size_t PART = 1 << 20;
+  static constexpr size_t PART = 2 << 20;
   struct Job {
     std::atomic<int> remaining{0};
     std::mutex mu;
@@ -509,7 +509,7 @@ class CopyPool {
 };
 
 struct Stager {
-  static constexpr size_t SLOT = 8u << 20;
+  static constexpr size_t SLOT = 32u << 20;
   static constexpr int NSLOT = 4;
   char* slot[NSLOT] = {};
   cudaEvent_t ev[NSLOT] = {};

@@ -181,15 +181,51 @@ GMSM_D uint32_t code_bucket(uint32_t code) { return (code >> 1) - 1u + (code & 1
 // once (one kernel for all windows) instead of one per scatter launch.
 // The loop is block-uniform and lanes past the end walk it with a zero scalar: every lane of a warp reaches the collectives.
 // The returning atomics of DIGIT_BATCH windows are issued back to back and consumed afterwards, so a thread waits for one
-// L2 round trip per batch instead of one per window (measured: 3.9 ms -> see DESIGN.md for n = 2^24, W = 15 with one
-// dependent round trip per window).
+// L2 round trip per batch instead of one per window.
+//
+// Warp aggregation costs a MATCH.ANY per digit, and that instruction iterates over the DISTINCT keys of the warp: ~32 rounds
+// for random digits (measured: K1 4.0 ms instead of 1.1 ms at n = 2^24), one round when they are all equal.  It is therefore
+// used only where it pays: (a) when a sampling pass over the scalars (k_skew_probe) found a value that owns more than 3 %
+// of the sample -- a global hot spot such as "smallvalues" --, or (b) for a batch of windows in which some lane holds the
+// same digit as its neighbour (runs of equal scalars, "redundancy"; one shuffle + one ballot per window to find out).
+// Everything else takes one plain returning atomicAdd per digit.
 static constexpr int DIGIT_BATCH = 8;
+static constexpr uint32_t PROBE_SAMPLES = 16384, PROBE_BINS = 2048;
+
+// flag[0] = 1 if one digit value of window 0 owns more than 1/32 of a strided sample of the scalars
+template <class G>
+__global__ void __launch_bounds__(256) k_skew_probe(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin, uint32_t* __restrict__ flag) {
+  __shared__ uint32_t bins[PROBE_BINS];
+  __shared__ uint32_t maxc;
+  for (uint32_t k = threadIdx.x; k < PROBE_BINS; k += blockDim.x) bins[k] = 0;
+  if (threadIdx.x == 0) maxc = 0;
+  __syncthreads();
+  const uint32_t S = n < PROBE_SAMPLES ? n : PROBE_SAMPLES;
+  const uint64_t stride = S ? (uint64_t)n / S : 1;
+  for (uint32_t k = threadIdx.x; k < S; k += blockDim.x) {
+    typename G::Fr s = load_vec_ro(scalars + (size_t)((uint64_t)k * stride));
+    if (s.is_zero()) continue;                    // zero scalars produce no entries
+    DigitStream<G> ds;
+    ds.init(s, c, nwin);
+    const uint32_t code = ds.next(0);
+    if (code) atomicAdd(&bins[(code * 2654435761u) >> 21], 1u);
+  }
+  __syncthreads();
+  uint32_t m = 0;
+  for (uint32_t k = threadIdx.x; k < PROBE_BINS; k += blockDim.x) m = max(m, bins[k]);
+  atomicMax(&maxc, m);
+  __syncthreads();
+  if (threadIdx.x == 0) flag[0] = (maxc * 32u > S && S >= 1024u) ? 1u : 0u;
+}
+
 template <class G>
 __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin,
-                              uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ ranks, uint32_t* __restrict__ hist) {
+                              uint32_t nb, uint32_t* __restrict__ digits, uint32_t* __restrict__ ranks, uint32_t* __restrict__ hist,
+                              const uint32_t* __restrict__ skew_flag) {
   using Fr = typename G::Fr;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt = (1u << lane) - 1u;
+  const bool agg_all = skew_flag[0] != 0;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i64 = base + threadIdx.x;
     const bool valid = i64 < n;
@@ -199,30 +235,41 @@ __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32
     DigitStream<G> ds;
     ds.init(s, c, nwin);       // (a zero scalar walks the windows like any other: all its digits are 0, multiexp.go:743)
     for (int j0 = 0; j0 < nwin; j0 += DIGIT_BATCH) {
-      uint32_t code[DIGIT_BATCH], first[DIGIT_BATCH];
-      unsigned peers[DIGIT_BATCH];
+      uint32_t code[DIGIT_BATCH];
+      bool agg = agg_all;
 #pragma unroll
       for (int b = 0; b < DIGIT_BATCH; b++) {
-        const int j = j0 + b;
-        code[b] = 0;
-        peers[b] = 0;
-        first[b] = 0;
-        if (j < nwin) {                                  // warp-uniform
-          code[b] = ds.next(j);
+        code[b] = (j0 + b < nwin) ? ds.next(j0 + b) : 0u;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, code[b], 1);
+        agg = agg || (__ballot_sync(0xffffffffu, lane != 0 && code[b] != 0 && code[b] == prev) != 0);
+      }
+      uint32_t first[DIGIT_BATCH];
+      if (agg) {                                           // warp-uniform
+        unsigned peers[DIGIT_BATCH];
+#pragma unroll
+        for (int b = 0; b < DIGIT_BATCH; b++) {
+          const int j = j0 + b;
           const uint32_t key = code[b] ? (uint32_t)j * nb + code_bucket(code[b]) : ID_NONE;
           peers[b] = __match_any_sync(0xffffffffu, key);
+          first[b] = 0;
           if (code[b] && (int)lane == __ffs((int)peers[b]) - 1) first[b] = atomicAdd(&hist[key], (uint32_t)__popc(peers[b]));
+        }
+#pragma unroll
+        for (int b = 0; b < DIGIT_BATCH; b++)
+          if (code[b]) first[b] = __shfl_sync(peers[b], first[b], __ffs((int)peers[b]) - 1) + (uint32_t)__popc(peers[b] & lt);
+      } else {
+#pragma unroll
+        for (int b = 0; b < DIGIT_BATCH; b++) {
+          first[b] = 0;
+          if (code[b]) first[b] = atomicAdd(&hist[(uint32_t)(j0 + b) * nb + code_bucket(code[b])], 1u);
         }
       }
 #pragma unroll
       for (int b = 0; b < DIGIT_BATCH; b++) {
         const int j = j0 + b;
-        if (j < nwin) {
-          if (code[b]) {
-            const uint32_t f = __shfl_sync(peers[b], first[b], __ffs((int)peers[b]) - 1);
-            ranks[(size_t)j * n + i] = f + (uint32_t)__popc(peers[b] & lt);
-          }
-          if (valid) digits[(size_t)j * n + i] = code[b];
+        if (j < nwin && valid) {
+          if (code[b]) ranks[(size_t)j * n + i] = first[b];
+          digits[(size_t)j * n + i] = code[b];
         }
       }
     }
@@ -405,6 +452,38 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 //   * bucket begins inside the chunk  -> the thread owns it: buckets[b] = sum
 //   * bucket began in an earlier chunk -> the partial goes to carries[t] (joined by k_carry_level)
 // ------------------------------------------------------------------------------------------
+// ---- bulk-asynchronous (TMA engine) staging of the NEXT base point -------------------------------------------------
+// GMSM_ACC_TMA = 1: the software pipeline of k_accumulate keeps the prefetched point in shared memory instead of in
+// registers.  Each thread owns one slot (one affine point) and one mbarrier; at the top of an iteration it posts
+//   mbarrier.arrive.expect_tx + cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes   (SASS: UBLKCP)
+// for the point of the following entry -- a 64..192-byte 1-D bulk copy executed by the TMA unit, no registers held while it
+// is in flight -- runs the mixed addition on the current point, then waits on the barrier's phase and reads the slot
+// (LDS.128).  This frees the 16 (G1, 8 limbs) .. 48 (bls12-381 G2) registers of `pt_next`.
+#ifndef GMSM_ACC_TMA
+#define GMSM_ACC_TMA 0
+#endif
+#if GMSM_ACC_TMA && defined(__CUDA_ARCH__)
+GMSM_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+GMSM_D void tma_bar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+GMSM_D void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot are ordered before the async write
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+GMSM_D void tma_bar_wait(uint32_t bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+  } while (!ok);
+}
+#endif
+
 #ifndef GMSM_ACC_MINBLOCKS_BIG
 #define GMSM_ACC_MINBLOCKS_BIG 1
 #endif
@@ -453,15 +532,29 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
 
   uint32_t e = entries[start];
   Affine<F> pt = load_vec_ro(points + (e >> 1));
+#if GMSM_ACC_TMA && defined(__CUDA_ARCH__)
+  __shared__ __align__(128) Affine<F> tma_slot[128];
+  __shared__ __align__(8) unsigned long long tma_bar[128];
+  const uint32_t slot_a = smem_u32(&tma_slot[threadIdx.x]), bar_a = smem_u32(&tma_bar[threadIdx.x]);
+  tma_bar_init(bar_a);
+  uint32_t tma_phase = 0;
+#endif
   for (uint32_t pos = start; pos < end; pos++) {
     // software pipeline: issue the next entry / point loads before the arithmetic of this one
     uint32_t e_next = 0;
-    Affine<F> pt_next;
     const bool has_next = (pos + 1 < end);
+#if GMSM_ACC_TMA && defined(__CUDA_ARCH__)
+    if (has_next) {
+      e_next = entries[pos + 1];
+      tma_load_1d(slot_a, points + (e_next >> 1), (uint32_t)sizeof(Affine<F>), bar_a);
+    }
+#else
+    Affine<F> pt_next;
     if (has_next) {
       e_next = entries[pos + 1];
       pt_next = load_vec_ro(points + (e_next >> 1));
     }
+#endif
     if (pos == bend) {
       // bucket boundary: flush, move to the bucket that contains `pos`
       if (owner) {
@@ -488,7 +581,13 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
     xyzz_add_mixed(acc, pt, (e & 1u) != 0);
     if (has_next) {
       e = e_next;
+#if GMSM_ACC_TMA && defined(__CUDA_ARCH__)
+      tma_bar_wait(bar_a, tma_phase);
+      tma_phase ^= 1u;
+      pt = load_vec(&tma_slot[threadIdx.x]);
+#else
       pt = pt_next;
+#endif
     }
   }
   if (owner) {

@@ -34,16 +34,35 @@ def gather_partials(local, world: int, group=None):
     return out
 
 
+def window_bits_for_total(curve: str, n_total: int) -> int:
+    """the window width every rank of a sharded MSM must use: derived ONCE from the total size (gmsm_choose_window_bits), never
+    from a rank's own shard -- uneven shards would otherwise pick different plans and their partials could not be added"""
+    from . import _native
+    from .multiexp import CURVES
+
+    return int(_native.lib().gmsm_choose_window_bits(CURVES[curve], int(n_total)))
+
+
 class ShardedMultiExp:
-    """engine + process group.  msm() returns the Jacobian triple (device tensor) on every rank."""
+    """engine + process group.  msm() returns the Jacobian triple (device tensor) on every rank.  All ranks must run the same
+    window plan: the constructor all-gathers (c, W) and refuses a mismatch (create the engines with
+    c = window_bits_for_total(curve, n_total))."""
 
     def __init__(self, engine, group=None):
+        import torch
         import torch.distributed as dist
 
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 1:
+            dev = torch.device("cuda", engine.device) if dist.get_backend(group) != "gloo" else torch.device("cpu")
+            mine = torch.tensor([engine.c, engine.nwin], dtype=torch.int64, device=dev)
+            plans = gather_partials(mine, self.world, group).cpu().view(self.world, 2)
+            if not bool((plans == plans[0]).all()):
+                raise ValueError("ranks run different window plans (c, W): %s -- create every engine with "
+                                 "c = window_bits_for_total(curve, n_total)" % plans.tolist())
 
     def msm_from_host(self, h_points, h_scalars, n_local: int, d_points_buf, d_scalars_buf, chunks: int = 4):
         """End-to-end sharded MSM from pinned host shards: the shard is cut into `chunks` batches; batch k+1

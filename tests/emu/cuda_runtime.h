@@ -167,6 +167,19 @@ static inline unsigned __match_any_sync(uint32_t mask, uint32_t key) {
   emu::group_barrier(w, gk, mask);
   return peers;
 }
+// full-warp vote (every live lane of the warp must call)
+static inline unsigned __ballot_sync(uint32_t mask, int pred) {
+  assert(emu::g_block && "__ballot_sync needs emu_launch_coop");
+  emu::Block& B = *emu::g_block;
+  const unsigned tid = B.cur, base = tid & ~31u, w = tid >> 5;
+  B.slot[tid] = pred ? 1u : 0u;
+  emu::group_barrier(w, 0, mask);
+  unsigned r = 0;
+  for (unsigned l = 0; l < 32; l++)
+    if (((mask >> l) & 1u) && base + l < B.nthreads && !B.done[base + l] && B.slot[base + l]) r |= 1u << l;
+  emu::group_barrier(w, 0, mask);
+  return r;
+}
 static inline void __syncwarp(uint32_t mask = 0xffffffffu) {
   assert(emu::g_block && "__syncwarp needs emu_launch_coop");
   emu::group_barrier(emu::g_block->cur >> 5, (unsigned)__builtin_ctz(mask), mask);

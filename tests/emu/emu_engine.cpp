@@ -30,6 +30,7 @@ struct Opts {
   int mode;           // bit 0: the real K1b scan kernels (block scans with warp shuffles) instead of a host scan
                       // bit 1: batch-affine bucket accumulation (affine_kernels.cuh, GMSM_AFFINE=1) instead of k_accumulate
                       // bit 2: every launch through the cooperative (fiber) launcher
+                      // bit 4: force K1's warp-aggregated atomics (as if the sampling pass had found a hot value)
                       // bit 3: the lane-parallel (quad) form of the tail kernels -- carry levels, segment reduction, group sums
 };
 
@@ -67,8 +68,10 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
     std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), ranks(n * (size_t)p.nwin + 16, 0xFFFFFFFFu),
         entries(n * (size_t)p.nwin + 16, 0);
     // (warp collectives -- __match_any_sync / __shfl_sync -- inside: always the cooperative launcher)
+    emu_launch_coop(k_skew_probe<G>, dim3(1), 256u, scalars, n32, p.c, p.nwin, hist.data() + nbp + 4);
+    if (o.mode & 16) hist[nbp + 4] = 1;    // force the warp-aggregated path everywhere
     emu_launch_coop(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256u, scalars, n32, p.c, p.nwin,
-                    shared ? 0u : p.nb, digits.data(), ranks.data(), hist.data());
+                    shared ? 0u : p.nb, digits.data(), ranks.data(), hist.data(), (const uint32_t*)(hist.data() + nbp + 4));
     // K1b: exclusive scan -- the three scan kernels (cooperative launch) or a host scan
     auto scan_u32 = [&](const uint32_t* in, uint32_t* out) {
       if (o.mode & 1) { real_scan(in, (uint32_t)nbp, out); return; }

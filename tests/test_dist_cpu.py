@@ -69,3 +69,42 @@ def test_shard_range_partitions():
             assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
     with pytest.raises(ValueError):
         distmod.shard_range(10, 2, 2)
+
+
+class _FakeEngine:
+    def __init__(self, c, nwin):
+        self.c, self.nwin, self.device = c, nwin, 0
+
+
+def _plan_worker(rank, world, port, q, plans):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    distmod = importlib.import_module("gnark-crypto_b200.dist")
+    try:
+        distmod.ShardedMultiExp(_FakeEngine(*plans[rank]))
+        q.put((rank, "ok"))
+    except ValueError as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("plans,ok", [([(17, 15), (17, 15)], True), ([(17, 15), (15, 17)], False)])
+def test_sharded_ranks_must_share_one_window_plan(plans, ok):
+    """ranks whose engines picked different window widths (uneven shards, c = 0) used to add partials of
+    different plans silently; ShardedMultiExp now all-gathers (c, W) and refuses a mismatch"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, q, plans)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, msg in res:
+        assert (msg == "ok") if ok else ("different window plans" in msg)

@@ -375,3 +375,23 @@ def test_emulated_quad_tail_skewed_and_all_equal():
         want, _, _, _ = cref.msm(g, pp, ss, c=0, nthreads=4)
         _check(g, emu_msm(g, pp, ss, 7, K=4, K2_first=2, K2=2, L=4, mode=8), want)
         _check(g, emu_msm(g, pp, ss, 7, K=4, K2_first=2, K2=2, L=4, mode=0), want)
+
+
+def test_emulated_k1_rank_numbering_paths():
+    """K1 numbers every entry inside its bucket with the returning atomicAdd that counts it (the scatter then needs no
+    atomics).  Three ways through it: plain atomics (random scalars), warp-aggregated atomics forced everywhere (mode bit 4),
+    and the two adaptive triggers -- runs of equal scalars (neighbouring lanes hold equal digits: "redundancy",
+    multiexp_test.go:327-334) and a global hot value found by the sampling pass ("smallvalues", :316-325: every 5th scalar
+    equal).  The emulated engine checks that the ranks of every bucket are a permutation of 0 .. count-1 (rc 10 otherwise)."""
+    g = "bn254_g1"
+    pts, s = make_inputs(g, 3000, 13, specials=False)
+    small = s.copy()
+    small[::5] = np.array([1, 0, 0, 0], dtype=np.uint64)
+    red = s.copy()
+    for i in range(0, 3000, 100):
+        red[i : i + 100] = red[i]
+    for scal in (s, small, red):
+        want, _, _, _ = cref.msm(g, pts, scal, c=0, nthreads=4)
+        for mode in (0, 16):
+            _check(g, emu_msm(g, pts, scal, 9, K=8, mode=mode), want)
+            _check(g, emu_msm(g, pts, scal, 6, tables=1, K=8, passes=2, mode=mode), want)
