@@ -75,35 +75,63 @@ static const GroupVTable* vtable(int curve) {
 }
 
 // ------------------------------------------------------------------------------------------
-// window-width model.  Cost in "mixed-add equivalents":
-//   accumulate: W * n            (one mixed add per non-zero digit)
-//   reduce    : nb_total * (2 full adds + scalar-mul/L) * 1.4  (full add ~ 1.4 mixed adds), at
-//               the lower parallel efficiency of the short reduce kernels (x RED_PENALTY)
-// constants calibrated on B200; c can be forced through gmsm_ctx_create / GMSM_C.
+// window-width model (the reference's bestC, multiexp.go:75-93, minimises (Bits + 1)(n + 2^c)/c over c <= 16 for a CPU whose
+// bucket array must stay in cache; the GPU's trade-off is different and is modelled from measurements).
+//   T(c) = n * W(c) * e_g(c)  +  tail_g(c)
+//   e_g(c)    time per bucket entry (one mixed addition + its share of the digit / sort passes): the measured accumulate rate
+//             of the group's kernel (multiplier-pipe bound), 1.2 % more per bit of c beyond 17 (the
+//             bucket array outgrows L2-friendly sizes), + 9 ps for K1 + the exposed part of the scatter
+//   tail_g(c) the n-independent stages -- carry join, bucket reduction (2^(c-1) W buckets: latency-bound below ~10^6 buckets,
+//             throughput-bound above), Horner over the windows, normalisation -- read from a table measured per group
+//             (profiles/r02_c_sweep_call3.txt: total - accumulate - digits - scatter of a width sweep), because its shape
+//             depends on occupancy steps of the tail kernels that no closed form captures
+// The table values are milliseconds on a B200 at 1965 MHz; on another part the argmin moves little because both terms scale
+// with the same clock.  Validation: profiles/r02_window_model_validation.md (the model's choice is within 2 % of the best
+// measured width for every swept configuration).  c can still be forced through gmsm_ctx_create / GMSM_C.
 // ------------------------------------------------------------------------------------------
-static int choose_c(int fr_bits, size_t n) {
+struct WidthModel {
+  double add_ns;          // accumulate: ns per mixed addition at c <= 17
+  double tail_ms[7];      // tail_g(c) for c = 13 .. 19
+};
+static const WidthModel& width_model(int curve) {
+  static const WidthModel bn254_g1 = {0.160, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}};
+  static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
+  static const WidthModel bn254_g2 = {0.599, {7.10, 6.96, 6.35, 6.50, 6.25, 10.2, 13.1}};
+  static const WidthModel bls_g2 = {1.353, {14.2, 13.9, 12.7, 13.0, 12.5, 20.4, 26.2}};
+  switch (curve) {
+    case GMSM_BN254_G1: return bn254_g1;
+    case GMSM_BLS12381_G1: case GMSM_BLS12377_G1: return bls_g1;
+    case GMSM_BN254_G2: return bn254_g2;
+    default: return bls_g2;
+  }
+}
+static double model_ms(int curve, int fr_bits, size_t n, int c) {
+  const WidthModel& m = width_model(curve);
+  const WindowPlan p = make_plan(fr_bits, c);
+  double tail;
+  if (c < 13) tail = m.tail_ms[0] * (1.0 + 0.03 * (13 - c));        // more windows: longer Horner / more launches, fewer buckets
+  else if (c > 19) tail = m.tail_ms[6] * (double)(1u << (c - 19));  // bucket reduction doubles per bit
+  else tail = m.tail_ms[c - 13];
+  // a last window of 1-2 bits (e.g. c = 23 for 254-bit scalars) puts all its entries on 1-2 buckets: never worth it
+  if (p.last_c <= 2 && p.nwin > 1) tail += 1e-6 * (double)n * 0.5;
+  const double e_ns = m.add_ns * (1.0 + 0.012 * std::max(0, c - 17)) + 0.009;
+  return (double)n * p.nwin * e_ns * 1e-6 + tail;
+}
+static int choose_c_for(int curve, int fr_bits, size_t n) {
   if (const char* e = getenv("GMSM_C")) {
     int c = atoi(e);
     if (c >= 2 && c <= 24) return c;
   }
-  // Measured on B200 (profiles/r01_c_sweep_all_v6.txt: bn254 G1 2^16..2^24, bls12-381 G1 2^22, bn254 G2
-  // 2^20/2^22): c = 17 (W = 15, lastC = 17) wins from n = 2^20 up for every group, c = 15 for 2^16..2^18;
-  // c = 18 keeps W = 15 but doubles the bucket reduction.  Below that the launch-latency floor (~3 ms)
-  // dominates and the analytic model is good enough.
-  if (n >= ((size_t)1 << 19)) return 17;
-  if (n >= ((size_t)1 << 14)) return 15;
   double best = 1e300;
-  int bc = 8;
-  for (int c = 4; c <= 16; c++) {
-    WindowPlan p = make_plan(fr_bits, c);
-    double acc = (double)p.nwin * (double)n;
-    double red = (double)p.nb_total * (2.0 + 22.0 / 32.0) * 1.4 * 3.0;
-    double sort_cost = (double)p.nwin * (double)n * 0.02;
-    double cost = acc + red + sort_cost;
-    if (cost < best) { best = cost; bc = c; }
+  int bc = 13;
+  for (int c = 4; c <= 22; c++) {
+    const double t = model_ms(curve, fr_bits, n, c);
+    if (t < best) { best = t; bc = c; }
   }
   return bc;
 }
+static int curve_of_bits_default(int fr_bits) { return fr_bits == 254 ? GMSM_BN254_G1 : (fr_bits == 255 ? GMSM_BLS12381_G1 : GMSM_BLS12377_G1); }
+static int choose_c(int fr_bits, size_t n) { return choose_c_for(curve_of_bits_default(fr_bits), fr_bits, n); }
 
 // window width of the window-table mode: one shared bucket set, so the bucket reduction costs 2^(c-1) * ~3.8
 // full-add equivalents ONCE instead of per window, and c can grow until that term meets the W(c)*n accumulate
@@ -249,7 +277,7 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   ctx->device = device;
   ctx->max_n = max_n;
   ctx->ci = ci;
-  if (c == 0) c = shared ? choose_c_tables(ci.fr_bits, max_n) : choose_c(ci.fr_bits, max_n);
+  if (c == 0) c = shared ? choose_c_tables(ci.fr_bits, max_n) : choose_c_for(curve, ci.fr_bits, max_n);
   ctx->shared = shared;
   // bucket accumulation: extended-Jacobian segmented reduction by default (INT-multiplier bound at 89 % of the
   // pipe); GMSM_AFFINE=1 selects the batch-affine tree (fewer multiplies, but 3x the HBM traffic: measured
@@ -654,7 +682,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
     P.scal_cap = n;
   }
   // window width from the TOTAL size (all batches share one bucket array); workspace sized for one batch
-  const int c = P.tables ? P.tab_c : (c_force ? c_force : choose_c(ci.fr_bits, n));
+  const int c = P.tables ? P.tab_c : (c_force ? c_force : choose_c_for(P.curve, ci.fr_bits, n));
   if (!P.ctx || P.ctx->max_n < nc || P.ctx->max_n > 4 * nc + 1024 || P.ctx->plan.c != c || P.ctx->shared != P.tables) {
     if (P.ctx) { gmsm_ctx_destroy(P.ctx); P.ctx = nullptr; }
     P.ctx = ctx_create_ex((gmsm_curve_t)P.curve, nc, c, P.device, P.tables);
@@ -942,7 +970,7 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   }
   // window-table mode: every shard carries the same table width and returns ONE partial
   const bool tables = jobs[0].sh->pipe.tables;
-  const int c = tables ? jobs[0].sh->pipe.tab_c : choose_c(ci.fr_bits, n);
+  const int c = tables ? jobs[0].sh->pipe.tab_c : choose_c_for(b->curve, ci.fr_bits, n);
   const WindowPlan plan = make_plan(ci.fr_bits, c);
   const size_t npart = tables ? 1 : (size_t)plan.nwin;
   std::vector<unsigned char> h_part(jobs.size() * npart * xb);
@@ -964,6 +992,42 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
     if (rcs[k]) return set_err(rcs[k], "device %d: %s", jobs[k].sh->device, errs[k].c_str());
   BaseShard& s0 = *jobs[0].sh;
   return join_partials(b->curve, s0.pipe, &s0.d_gather, &s0.gather_cap, h_part.data(), h_part.size(), (int)jobs.size(), out_jac);
+}
+
+// MSM over resident bases with scalars that are ALREADY on the device (the output of a device-side iFFT, gmsm_fft_device:
+// prover scalars then never cross PCIe -- SURVEY.md section 8(f) N3).  d_scalars: n x 32 bytes, Montgomery form, on the
+// device that holds the bases (single-shard handles only); the work is enqueued on `stream` after whatever the caller put
+// there (e.g. the FFT) and the call returns when the result is on the host.
+extern "C" int gmsm_bases_multiexp_device(gmsm_bases_t* b, size_t offset, const void* d_scalars, size_t n, int nb_tasks,
+                                          uint64_t* out_jac, void* stream) {
+  if (!b) return set_err(GMSM_EINVAL, "null bases");
+  if (int rc = check_nb_tasks(nb_tasks)) return rc;
+  if (offset > b->n || n > b->n - offset) return set_err(GMSM_EINVAL, "len(points) != len(scalars)");
+  if (b->shards.size() != 1) return set_err(GMSM_EINVAL, "device scalars need bases that live on one device (this handle is sharded over %zu)", b->shards.size());
+  std::lock_guard<std::mutex> lk(b->mu);
+  CurveInfo ci;
+  curve_info(b->curve, &ci);
+  const size_t ab = 8u * ci.coord_words, jb = 12u * ci.coord_words;
+  if (n == 0) { memset(out_jac, 0, jb); return GMSM_OK; }
+  BaseShard& sh = b->shards[0];
+  Pipeline& P = sh.pipe;
+  CK(cudaSetDevice(P.device));
+  const int c = P.tables ? P.tab_c : choose_c_for(P.curve, ci.fr_bits, n);
+  if (!P.ctx || P.ctx->max_n < n || P.ctx->max_n > 4 * n + 1024 || P.ctx->plan.c != c || P.ctx->shared != P.tables) {
+    if (P.ctx) { gmsm_ctx_destroy(P.ctx); P.ctx = nullptr; }
+    P.ctx = ctx_create_ex((gmsm_curve_t)P.curve, n, c, P.device, P.tables);
+    if (!P.ctx) return GMSM_ECUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (P.tables)
+    rc = gmsm_ctx_msm_tables_device(P.ctx, sh.d_points, P.tab_stride, offset, d_scalars, n, P.d_out, st);
+  else
+    rc = gmsm_ctx_msm_device(P.ctx, reinterpret_cast<const char*>(sh.d_points) + offset * ab, d_scalars, n, P.d_out, st);
+  if (rc) { cudaStreamSynchronize(st); return rc; }
+  CK(cudaMemcpyAsync(out_jac, P.d_out, jb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GMSM_OK;
 }
 
 // Sessions of the host entry points: device buffers, streams, the pinned ring and the engine context are kept between
@@ -1032,7 +1096,7 @@ static int session_prepare(Session& S, int curve, int device, size_t cnt) {
 extern "C" int gmsm_choose_window_bits(gmsm_curve_t curve, size_t n_total) {
   CurveInfo ci;
   if (!curve_info(curve, &ci)) return 0;
-  return choose_c(ci.fr_bits, n_total);
+  return choose_c_for(curve, ci.fr_bits, n_total);
 }
 
 // one shard of a sharded call, host buffers in, W window partials (host) out: the pipelined engine of
@@ -1075,7 +1139,7 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
     return pipeline_run(lease.S->pipe, lease.S->d_points, points, scalars, n, out_jac);
   }
   // ---- multi-device: contiguous shards (the reference's recursive halving, multiexp.go:128-140) ----
-  const int c = choose_c(ci.fr_bits, n);
+  const int c = choose_c_for(curve, ci.fr_bits, n);
   const WindowPlan plan = make_plan(ci.fr_bits, c);
   const size_t xb = 16u * ci.coord_words;
   std::vector<unsigned char> h_part(D * plan.nwin * xb);

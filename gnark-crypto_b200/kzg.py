@@ -429,3 +429,27 @@ def decode_g1_points(curve: str, data: bytes, n: int, raw: bool = False, check_o
     if rc != 0:
         raise MultiExpError(_native.last_error())
     return out
+
+
+def CommitLagrange(evals, pk: ProvingKey, domain) -> np.ndarray:
+    """Digest of the polynomial given by its values on `domain` (fft.Domain of this package): the evaluations go to the device
+    once, FFTInverse(DIF) + BitReverse (fft.go:111-190, bitreverse.go:17-42) run there and their output -- the coefficients,
+    still in device memory, Montgomery form -- feeds the MultiExp directly (gmsm_bases_multiexp_device): the canonical-form
+    coefficients never visit the host.  Equals Commit(FFTInverse(evals), pk)."""
+    import torch
+
+    from .fft import DIF
+
+    ev = np.ascontiguousarray(evals, dtype=np.uint64).reshape(-1, 4)
+    if ev.shape[0] != domain.Cardinality:
+        raise MultiExpError("len(a) must equal the domain cardinality")
+    if ev.shape[0] == 0 or ev.shape[0] > pk.G1.shape[0]:
+        raise ErrInvalidPolynomialSize("invalid polynomial size (larger than SRS or == 0)")
+    dev = torch.device("cuda", domain.device)
+    d = torch.from_numpy(ev.view(np.int64).reshape(-1).copy()).to(dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    domain.fft_device(d, True, DIF, False, st)          # natural in, bit-reversed out
+    domain.bit_reverse_device(d, st)
+    jac = pk._bases.MultiExpDevice(d, ev.shape[0], stream=st)
+    w = pk.words
+    return jac[:w].copy() if jac[w:].any() else np.zeros(w, dtype=np.uint64)

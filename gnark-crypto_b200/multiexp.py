@@ -176,6 +176,17 @@ class ResidentBases:
         _check(rc)
         return out
 
+    def MultiExpDevice(self, d_scalars, n: int = None, config: MultiExpConfig = None, offset: int = 0, stream=None):
+        """the same with scalars already on the device (torch int64 tensor in fr.Element layout, e.g. straight out of
+        fft.Domain.fft_device): nothing but the 96..288-byte result crosses PCIe"""
+        config = config or MultiExpConfig()
+        if n is None:
+            n = d_scalars.numel() // 4
+        out = np.zeros(3 * self.w, dtype=np.uint64)
+        rc = _native.lib().gmsm_bases_multiexp_device(self._h, offset, d_scalars.data_ptr(), n, int(config.NbTasks), out.ctypes.data, stream)
+        _check(rc)
+        return out
+
     def Precompute(self, c: int = 0) -> int:
         """gmsm_bases_precompute: replace the device copy of the bases by window tables (row j = 2^(c*j) * bases);
         later MultiExp calls are bit-identical and ~20 % faster.  Returns the table window width."""

@@ -97,6 +97,11 @@ gmsm_bases_t* gmsm_bases_upload(gmsm_curve_t curve, const uint64_t* points, size
 int gmsm_bases_multiexp(gmsm_bases_t* bases, size_t offset, const uint64_t* scalars, size_t n,
                         int nb_tasks, uint64_t* out_jac);
 void gmsm_bases_free(gmsm_bases_t* bases);
+/* the same with scalars that are already in device memory (e.g. the output of gmsm_fft_device: iFFT -> fromMont -> digits
+ * without a PCIe crossing); d_scalars lives on the device of the (single-shard) bases, the work is
+ * ordered after `stream`'s earlier work, the result comes back to the host */
+int gmsm_bases_multiexp_device(gmsm_bases_t* bases, size_t offset, const void* d_scalars, size_t n, int nb_tasks,
+                               uint64_t* out_jac, void* stream);
 /* Window tables for resident bases (no reference counterpart: the reference re-reads its bases on every call; this
  * serves the static-SRS flow of kzg.Commit, kzg/kzg.go:159-176).  Replaces the device copy of the bases by a table of
  * W rows, row j = 2^(c*j) * bases (W x the device memory, built once on the GPU).  Afterwards gmsm_bases_multiexp

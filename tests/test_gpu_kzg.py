@@ -115,3 +115,32 @@ def test_device_point_decoding_matches_host_set_bytes(curve, g):
     bad5[3 * 2 * nb:3 * 2 * nb + nb] = bytes([~kzg._FLAGS[c]["mask"] & 0xFF]) + b"\xff" * (nb - 1)   # x >= q, flag bits zero (uncompressed)
     with pytest.raises(kzg.MultiExpError, match="point 3: invalid fp.Element encoding"):
         kzg.decode_g1_points(c, bytes(bad5), n, raw=True)
+
+
+def test_commit_from_lagrange_values_stays_on_the_device():
+    """next-row N3 -> N2 fusion: evaluations -> FFTInverse + BitReverse on the device -> MultiExp over resident bases with the
+    device-resident coefficients (gmsm_bases_multiexp_device) == Commit of the host iFFT == [f(alpha)]G"""
+    kzg = import_module("gnark-crypto_b200.kzg")
+    fft = import_module("gnark-crypto_b200.fft")
+    g = "bn254_g1"
+    G = O.GROUPS[g]
+    r = G.fr.q
+    size, alpha = 4096, 0xBEEF1234567
+    gen = G.encode_affine([G.gen])[0]
+    srs = kzg.new_srs_g1("bn254", size, alpha, gen, r, G.encode_scalars)
+    pk = kzg.ProvingKey("bn254", srs)
+    dom = fft.NewDomain("bn254", size)
+    rng = np.random.default_rng(5)
+    coeffs = [int(x) for x in rng.integers(0, 2**62, size=size)]
+    evals = G.encode_scalars(coeffs)                 # take them as coefficients, move to evaluations with the host-buffer FFT
+    dom.FFT(evals, fft.DIF)
+    ev_nat = evals.copy()
+    # bit-reverse on the host to natural order (DIF output is bit-reversed)
+    idx = np.array([int(format(i, "012b")[::-1], 2) for i in range(size)])
+    ev_nat = evals[idx]
+    digest = kzg.CommitLagrange(ev_nat, pk, dom)
+    f_alpha = sum(c * pow(alpha, i, r) for i, c in enumerate(coeffs)) % r
+    assert np.array_equal(digest, cref.scalar_mul(g, gen, f_alpha))
+    assert np.array_equal(digest, kzg.Commit(G.encode_scalars(coeffs), pk))
+    pk.close()
+    dom.close()
