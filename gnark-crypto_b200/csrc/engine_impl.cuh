@@ -38,7 +38,7 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   CK(cudaMemsetAsync(c->hist, 0, (nbp + 8) * 4, st));
   {
     unsigned blocks = std::min<unsigned>(nblk(n, 256), 148u * 16u);
-    k_skew_probe<G><<<1, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->hist + nbp + 4);    // flag lives in the pad of hist[] (just cleared)
+    k_skew_probe<G><<<PROBE_BLOCKS, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->hist + nbp + 4);    // flag lives in the pad of hist[] (just cleared)
     k_digits_hist<G><<<blocks, 256, 0, st>>>(scalars, n32, p.c, p.nwin, c->shared ? 0u : p.nb, c->digits, c->ranks, c->hist, c->hist + nbp + 4);
     launches++;
     launches++;
@@ -80,8 +80,8 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
       const uint32_t blo = std::min<uint64_t>((uint64_t)r * range_sz, p.nb_total);
       const uint32_t bhi = std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
       if (blo >= bhi) return;
-      k_scatter_shared<<<dim3(blocks, (unsigned)p.nwin), 256, 0, s>>>(c->digits, c->ranks, n32, c->tab_stride, c->offsets,
-                                                                       c->entries, blo, bhi);
+      k_scatter_shared<<<dim3(blocks, (unsigned)p.nwin), 256, 0, s>>>(c->digits, c->ranks, n32, c->tab_stride, c->hist, c->offsets,
+                                                                       c->entries, blo, bhi, c->hist + nbp + 4);
       launches++;
     };
     if (SPLIT_W < NPASS) {
@@ -95,8 +95,8 @@ static int run_accumulate(gmsm_ctx* c, const void* d_points, const void* d_scala
   } else {
     unsigned blocks = std::min<unsigned>(nblk(n, 256 * 4), 148u * 8u);
     auto scatter = [&](int j, cudaStream_t s) {
-      k_scatter_window<<<blocks, 256, 0, s>>>(c->digits + (size_t)j * n, c->ranks + (size_t)j * n, n32,
-                                              c->offsets + (size_t)j * p.nb, c->entries);
+      k_scatter_window<<<blocks, 256, 0, s>>>(c->digits + (size_t)j * n, c->ranks + (size_t)j * n, n32, c->hist + (size_t)j * p.nb,
+                                              c->offsets + (size_t)j * p.nb, c->entries, c->hist + nbp + 4);
       launches++;
     };
     if (SPLIT_W < NPASS) {

@@ -32,9 +32,19 @@ GMSM_HD Fp<P> fp_mul_by5(const Fp<P>& c) {  // fp.MulBy5
 }
 
 // Karatsuba, 3 fp.Mul (e2_bn254.go:28-38; e2_bls377.go:12-23 with the a1*b1 term times 5)
+// GMSM_FP2_DOT2 = 1 (experimental): z0 = x0 y0 + x1 (beta y1) and z1 = x0 y1 + x1 y0 as two fused two-product reductions
+// (fp_dot2, field.cuh): 4 products + 2 reductions = 400 IMAD.WIDE for N = 8 against Karatsuba's 3 x 136 = 408, without the
+// five additions / subtractions Karatsuba pays around its products.  Same unique reduced values.
 template <class P>
 GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
   static_assert(P::FP2_NONRES == -1 || P::FP2_NONRES == -5, "supported quadratic non-residues");
+#if defined(GMSM_FP2_DOT2) && defined(GMSM_DOT2)
+  Fp2<P> z;
+  const Fp<P> by1 = (P::FP2_NONRES == -5) ? fp_neg(fp_mul_by5(y.a1)) : fp_neg(y.a1);
+  z.a0 = fp_dot2(x.a0, y.a0, x.a1, by1);
+  z.a1 = fp_dot2(x.a0, y.a1, x.a1, y.a0);
+  return z;
+#else
   Fp<P> a = fp_add(x.a0, x.a1);
   Fp<P> b = fp_add(y.a0, y.a1);
   a = fp_mul(a, b);
@@ -45,6 +55,7 @@ GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
   if (P::FP2_NONRES == -5) c = fp_mul_by5(c);
   z.a0 = fp_sub(b, c);
   return z;
+#endif
 }
 
 // 2 fp.Mul (e2_bn254.go:41-51; e2_bls377.go:26-38: (a0+a1)(a0-5a1) + 4 a0 a1)

@@ -3,7 +3,7 @@
 // Pipeline (replaces ecc/bn254/multiexp.go:148-209 `_innerMsmG1` and its callees):
 //   K1  k_digits_hist      partitionScalars (multiexp.go:709-803) fused with a bucket histogram
 //   K1b k_scan_*           exclusive scan of the histogram -> bucket offsets
-//   K1c k_scatter_window   digits + ranks -> entries grouped by bucket (no atomics: K1 numbered them)
+//   K1c k_scatter_window   digits -> entries grouped by bucket (positions from K1's ranks, or from a returning atomic)
 //   K2  k_accumulate       bucket accumulation (processChunk, multiexp_jacobian.go:20-39) as a
 //                          load-balanced segmented reduction over the bucket-ordered entry list
 //   K2b k_carry_level      joins partial sums of buckets that span several chunks
@@ -172,39 +172,50 @@ GMSM_D void for_each_digit(const typename G::Fr& s_mont, int c, int nwin, Fn fn)
 // bucket index inside its window for a non-zero code: magnitude - 1
 GMSM_D uint32_t code_bucket(uint32_t code) { return (code >> 1) - 1u + (code & 1u); }
 
-// K1: digits (stored chunk-major, digits[j*n + i], the reference's layout multiexp.go:785) + histogram + the RANK of every
-// entry inside its bucket (ranks[j*n + i]): the returning atomicAdd that counts the bucket also numbers its entries, so
-// the scatter (K1c) needs no atomics at all.  The atomics are warp-aggregated: lanes of a warp that hit the same bucket
-// (__match_any_sync) send ONE atomicAdd of their count and number themselves locally.  Skewed inputs -- the reference's
-// "redundancy" benchmark (runs of 100 equal scalars) or "smallvalues" (n/5 equal scalars), multiexp_test.go:316-334 --
-// otherwise put millions of atomics on a handful of addresses; here all W hot addresses of such an input are in flight at
-// once (one kernel for all windows) instead of one per scatter launch.
-// The loop is block-uniform and lanes past the end walk it with a zero scalar: every lane of a warp reaches the collectives.
-// The returning atomics of DIGIT_BATCH windows are issued back to back and consumed afterwards, so a thread waits for one
-// L2 round trip per batch instead of one per window.
+// K1: digits (stored chunk-major, digits[j*n + i], the reference's layout multiexp.go:785) + bucket histogram.
 //
-// Warp aggregation costs a MATCH.ANY per digit, and that instruction iterates over the DISTINCT keys of the warp: ~32 rounds
-// for random digits (measured: K1 4.0 ms instead of 1.1 ms at n = 2^24), one round when they are all equal.  It is therefore
-// used only where it pays: (a) when a sampling pass over the scalars (k_skew_probe) found a value that owns more than 3 %
-// of the sample -- a global hot spot such as "smallvalues" --, or (b) for a batch of windows in which some lane holds the
-// same digit as its neighbour (runs of equal scalars, "redundancy"; one shuffle + one ballot per window to find out).
-// Everything else takes one plain returning atomicAdd per digit.
+// The counting sort that follows needs, for every entry, its position inside its bucket.  Two modes, chosen per call by a
+// sampling pass over the scalars (k_skew_probe -> flag in device memory, read by K1 and by the scatter kernels):
+//   * plain mode (flag = 0, random-looking scalars): K1 counts with fire-and-forget atomics (RED) and the scatter takes the
+//     positions with a returning atomicSub per entry -- most of the scatter runs on the auxiliary stream underneath the
+//     accumulate kernel, so its atomics are off the critical path.
+//   * rank mode (flag = 1, skewed scalars): K1's atomic RETURNS, which numbers the entry inside its bucket (ranks[j*n + i]),
+//     and is warp-aggregated -- lanes of a warp that hit the same bucket (__match_any_sync) send ONE atomicAdd of their count and
+//     number themselves locally; the scatter then needs no atomics at all.  Skewed inputs -- the reference's "redundancy"
+//     benchmark (runs of 100 equal scalars) or "smallvalues" (n/5 equal scalars), multiexp_test.go:316-334 -- otherwise put
+//     millions of atomics on a handful of addresses, one window per scatter launch; here all W hot addresses are in flight at
+//     once and 32 equal lanes cost one atomic.
+// Why not always rank mode: MATCH.ANY iterates over the DISTINCT keys of a warp (~32 rounds for random digits) and returning
+// atomics cost about twice a RED: measured 4.0 ms (aggregated) / 2.25 ms (plain returning) against 1.3 ms for the RED
+// histogram at n = 2^24, W = 15 (profiles/r02_*).  In rank mode the returning atomics of DIGIT_BATCH windows are issued back to
+// back and consumed afterwards (one L2 round trip per batch).  Lanes past the end walk the loop with a zero scalar so that
+// every lane of a warp reaches the collectives.
 static constexpr int DIGIT_BATCH = 8;
 static constexpr uint32_t PROBE_SAMPLES = 16384, PROBE_BINS = 2048;
 
-// flag[0] = 1 if one digit value of window 0 owns more than 1/32 of a strided sample of the scalars
+// flag[0] |= 1 if, in this block's strided sample of the scalars (PROBE_BLOCKS blocks x PROBE_PER_BLOCK samples), one digit value
+// of window 0 owns more than 1/32 of the sample (a global hot spot) or more than 1/32 of the sampled scalars equal their
+// successor (runs of equal scalars).  flag[] is cleared with the histogram before every call.
+static constexpr uint32_t PROBE_BLOCKS = 16, PROBE_PER_BLOCK = PROBE_SAMPLES / PROBE_BLOCKS;
 template <class G>
 __global__ void __launch_bounds__(256) k_skew_probe(const typename G::Fr* __restrict__ scalars, uint32_t n, int c, int nwin, uint32_t* __restrict__ flag) {
   __shared__ uint32_t bins[PROBE_BINS];
-  __shared__ uint32_t maxc;
+  __shared__ uint32_t maxc, pairs;
   for (uint32_t k = threadIdx.x; k < PROBE_BINS; k += blockDim.x) bins[k] = 0;
-  if (threadIdx.x == 0) maxc = 0;
+  if (threadIdx.x == 0) { maxc = 0; pairs = 0; }
   __syncthreads();
-  const uint32_t S = n < PROBE_SAMPLES ? n : PROBE_SAMPLES;
+  const uint32_t S = n < PROBE_SAMPLES ? n : PROBE_SAMPLES;          // samples of the whole grid
   const uint64_t stride = S ? (uint64_t)n / S : 1;
-  for (uint32_t k = threadIdx.x; k < S; k += blockDim.x) {
-    typename G::Fr s = load_vec_ro(scalars + (size_t)((uint64_t)k * stride));
+  const uint32_t k_lo = blockIdx.x * PROBE_PER_BLOCK, k_hi = (k_lo + PROBE_PER_BLOCK < S) ? k_lo + PROBE_PER_BLOCK : S;
+  const uint32_t mine = k_hi > k_lo ? k_hi - k_lo : 0;
+  for (uint32_t k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
+    const size_t i = (size_t)((uint64_t)k * stride);
+    typename G::Fr s = load_vec_ro(scalars + i);
     if (s.is_zero()) continue;                    // zero scalars produce no entries
+    if (i + 1 < n) {
+      typename G::Fr t = load_vec_ro(scalars + i + 1);
+      if (t == s) atomicAdd(&pairs, 1u);
+    }
     DigitStream<G> ds;
     ds.init(s, c, nwin);
     const uint32_t code = ds.next(0);
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(256) k_skew_probe(const typename G::Fr* __rest
   for (uint32_t k = threadIdx.x; k < PROBE_BINS; k += blockDim.x) m = max(m, bins[k]);
   atomicMax(&maxc, m);
   __syncthreads();
-  if (threadIdx.x == 0) flag[0] = (maxc * 32u > S && S >= 1024u) ? 1u : 0u;
+  if (threadIdx.x == 0 && mine >= 256u && (maxc * 32u > mine || pairs * 32u > mine)) atomicOr(flag, 1u);
 }
 
 template <class G>
@@ -225,48 +236,40 @@ __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32
   using Fr = typename G::Fr;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt = (1u << lane) - 1u;
-  const bool agg_all = skew_flag[0] != 0;
+  const bool rank_mode = skew_flag[0] != 0;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i64 = base + threadIdx.x;
     const bool valid = i64 < n;
     const uint32_t i = (uint32_t)i64;
     Fr s = Fr::zero();
     if (valid) s = load_vec_ro(scalars + i);
+    if (!rank_mode) {
+      // plain mode: count only (the scatter numbers the entries)
+      if (valid)
+        for_each_digit<G>(s, c, nwin, [&](int j, uint32_t code) {
+          digits[(size_t)j * n + i] = code;
+          if (code) atomicAdd(&hist[(uint32_t)j * nb + code_bucket(code)], 1u);
+        });
+      continue;
+    }
     DigitStream<G> ds;
     ds.init(s, c, nwin);       // (a zero scalar walks the windows like any other: all its digits are 0, multiexp.go:743)
     for (int j0 = 0; j0 < nwin; j0 += DIGIT_BATCH) {
-      uint32_t code[DIGIT_BATCH];
-      bool agg = agg_all;
+      uint32_t code[DIGIT_BATCH], first[DIGIT_BATCH];
+      unsigned peers[DIGIT_BATCH];
 #pragma unroll
       for (int b = 0; b < DIGIT_BATCH; b++) {
-        code[b] = (j0 + b < nwin) ? ds.next(j0 + b) : 0u;
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, code[b], 1);
-        agg = agg || (__ballot_sync(0xffffffffu, lane != 0 && code[b] != 0 && code[b] == prev) != 0);
-      }
-      uint32_t first[DIGIT_BATCH];
-      if (agg) {                                           // warp-uniform
-        unsigned peers[DIGIT_BATCH];
-#pragma unroll
-        for (int b = 0; b < DIGIT_BATCH; b++) {
-          const int j = j0 + b;
-          const uint32_t key = code[b] ? (uint32_t)j * nb + code_bucket(code[b]) : ID_NONE;
-          peers[b] = __match_any_sync(0xffffffffu, key);
-          first[b] = 0;
-          if (code[b] && (int)lane == __ffs((int)peers[b]) - 1) first[b] = atomicAdd(&hist[key], (uint32_t)__popc(peers[b]));
-        }
-#pragma unroll
-        for (int b = 0; b < DIGIT_BATCH; b++)
-          if (code[b]) first[b] = __shfl_sync(peers[b], first[b], __ffs((int)peers[b]) - 1) + (uint32_t)__popc(peers[b] & lt);
-      } else {
-#pragma unroll
-        for (int b = 0; b < DIGIT_BATCH; b++) {
-          first[b] = 0;
-          if (code[b]) first[b] = atomicAdd(&hist[(uint32_t)(j0 + b) * nb + code_bucket(code[b])], 1u);
-        }
+        const int j = j0 + b;
+        code[b] = (j < nwin) ? ds.next(j) : 0u;
+        const uint32_t key = code[b] ? (uint32_t)j * nb + code_bucket(code[b]) : ID_NONE;
+        peers[b] = __match_any_sync(0xffffffffu, key);
+        first[b] = 0;
+        if (code[b] && (int)lane == __ffs((int)peers[b]) - 1) first[b] = atomicAdd(&hist[key], (uint32_t)__popc(peers[b]));
       }
 #pragma unroll
       for (int b = 0; b < DIGIT_BATCH; b++) {
         const int j = j0 + b;
+        if (code[b]) first[b] = __shfl_sync(peers[b], first[b], __ffs((int)peers[b]) - 1) + (uint32_t)__popc(peers[b] & lt);
         if (j < nwin && valid) {
           if (code[b]) ranks[(size_t)j * n + i] = first[b];
           digits[(size_t)j * n + i] = code[b];
@@ -276,12 +279,15 @@ __global__ void k_digits_hist(const typename G::Fr* __restrict__ scalars, uint32
   }
 }
 
-// K1c: scatter of ONE window, no atomics: entries[offsets[b] + rank] = (i << 1) | sign.  Launched window by window so that
-// the randomly written slice of `entries` (<= 4n bytes) stays L2-resident (126 MB) and reaches HBM once, as full lines,
-// instead of one read-modify-write per 4-byte store.
+// K1c: scatter of ONE window: entries[offsets[b] + position] = (i << 1) | sign, the position taken from ranks[] (rank mode) or
+// with a returning atomicSub on the bucket's counter (plain mode: filled from the back, the histogram counts down to zero).
+// Launched window by window so that the randomly written slice of `entries` (<= 4n bytes) and the window's counters stay
+// L2-resident (126 MB) and reach HBM once, as full lines, instead of one read-modify-write per 4-byte store.
 static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, const uint32_t* __restrict__ ranks_w, uint32_t n,
-                                        const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries) {
-  constexpr int U = 4;   // independent elements per thread and iteration
+                                        uint32_t* __restrict__ hist_w, const uint32_t* __restrict__ offsets_w, uint32_t* __restrict__ entries,
+                                        const uint32_t* __restrict__ skew_flag) {
+  constexpr int U = 4;   // independent elements per thread and iteration (the plain mode is bound by the round trip of its atomics)
+  const bool rank_mode = skew_flag[0] != 0;
   const uint32_t tile = blockDim.x * U;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n; base += (uint64_t)gridDim.x * tile) {
     uint32_t code[U], rk[U], off[U];
@@ -289,11 +295,16 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, c
     for (int u = 0; u < U; u++) {
       const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
       code[u] = (i < n) ? __ldg(digits_w + i) : 0u;
-      rk[u] = (i < n) ? __ldg(ranks_w + i) : 0u;     // (unwritten where code == 0: never used)
+      rk[u] = (rank_mode && code[u]) ? __ldg(ranks_w + i) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++)
-      if (code[u]) off[u] = offsets_w[code_bucket(code[u])];
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t b = code_bucket(code[u]);
+        if (!rank_mode) rk[u] = atomicSub(&hist_w[b], 1u) - 1u;
+        off[u] = offsets_w[b];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (code[u]) {
@@ -310,8 +321,10 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, c
 // [blo, bhi): a range owns a contiguous slice of `entries` (~4n bytes for uniform digits), every pass streams
 // all n*W digits (coalesced) and scatters only the ones of its range.  blockIdx.y = window.
 static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, const uint32_t* __restrict__ ranks, uint32_t n, uint32_t row_stride,
-                                        const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries, uint32_t blo, uint32_t bhi) {
+                                        uint32_t* __restrict__ hist, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries,
+                                        uint32_t blo, uint32_t bhi, const uint32_t* __restrict__ skew_flag) {
   constexpr int U = 4;
+  const bool rank_mode = skew_flag[0] != 0;
   const uint32_t tile = blockDim.x * U;
   const uint32_t j = blockIdx.y;
   const uint32_t* digits_w = digits + (size_t)j * n;
@@ -327,11 +340,16 @@ static __global__ void k_scatter_shared(const uint32_t* __restrict__ digits, con
         const uint32_t b = code_bucket(code[u]);
         if (b < blo || b >= bhi) code[u] = 0u;
       }
-      rk[u] = code[u] ? __ldg(ranks_w + i) : 0u;
+      rk[u] = (rank_mode && code[u]) ? __ldg(ranks_w + i) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++)
-      if (code[u]) off[u] = offsets[code_bucket(code[u])];
+    for (int u = 0; u < U; u++) {
+      if (code[u]) {
+        const uint32_t b = code_bucket(code[u]);
+        if (!rank_mode) rk[u] = atomicSub(&hist[b], 1u) - 1u;
+        off[u] = offsets[b];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (code[u]) {

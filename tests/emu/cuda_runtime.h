@@ -50,6 +50,7 @@ static inline unsigned long long __brevll(unsigned long long v) {
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
 }
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline uint32_t atomicMax(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = std::max(o, v); return o; }
 using std::max;
 using std::min;

@@ -68,8 +68,9 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
     std::vector<uint32_t> hist(nbp + 8, 0), offsets(nbp + 8, 0), digits(n * (size_t)p.nwin + 16, 0), ranks(n * (size_t)p.nwin + 16, 0xFFFFFFFFu),
         entries(n * (size_t)p.nwin + 16, 0);
     // (warp collectives -- __match_any_sync / __shfl_sync -- inside: always the cooperative launcher)
-    emu_launch_coop(k_skew_probe<G>, dim3(1), 256u, scalars, n32, p.c, p.nwin, hist.data() + nbp + 4);
-    if (o.mode & 16) hist[nbp + 4] = 1;    // force the warp-aggregated path everywhere
+    emu_launch_coop(k_skew_probe<G>, dim3(PROBE_BLOCKS), 256u, scalars, n32, p.c, p.nwin, hist.data() + nbp + 4);
+    if (o.mode & 16) hist[nbp + 4] = 1;    // force the rank mode (as if the sampling pass had found skewed scalars)
+    if (o.mode & 32) hist[nbp + 4] = 0;    // force the plain mode
     emu_launch_coop(k_digits_hist<G>, dim3(std::min<unsigned>(nblk(n, 256), 148u * 16u)), 256u, scalars, n32, p.c, p.nwin,
                     shared ? 0u : p.nb, digits.data(), ranks.data(), hist.data(), (const uint32_t*)(hist.data() + nbp + 4));
     // K1b: exclusive scan -- the three scan kernels (cooperative launch) or a host scan
@@ -89,18 +90,17 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
         const uint32_t bhi = (uint32_t)std::min<uint64_t>((uint64_t)(r + 1) * range_sz, p.nb_total);
         if (blo >= bhi) continue;
         LAUNCH(k_scatter_shared, dim3(std::min<unsigned>(nblk(n, 1024), 296u), (unsigned)p.nwin), 256, (const uint32_t*)digits.data(),
-                   (const uint32_t*)ranks.data(), n32, row_stride, (const uint32_t*)offsets.data(), entries.data(), blo, bhi);
+                   (const uint32_t*)ranks.data(), n32, row_stride, hist.data(), (const uint32_t*)offsets.data(), entries.data(), blo, bhi,
+                   (const uint32_t*)(hist.data() + nbp + 4));
       }
     } else {
       for (int j = 0; j < p.nwin; j++)
         LAUNCH(k_scatter_window, dim3(std::min<unsigned>(nblk(n, 1024), 148u * 8u)), 256, (const uint32_t*)(digits.data() + (size_t)j * n),
-                   (const uint32_t*)(ranks.data() + (size_t)j * n), n32, (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data());
+                   (const uint32_t*)(ranks.data() + (size_t)j * n), n32, hist.data() + (size_t)j * p.nb,
+                   (const uint32_t*)(offsets.data() + (size_t)j * p.nb), entries.data(), (const uint32_t*)(hist.data() + nbp + 4));
     }
-    // the ranks K1 handed out number every bucket's entries 0 .. count-1 exactly once: the scatter filled offsets[b] .. offsets[b+1]
-    // without holes or collisions iff every slot below offsets[nb_total] was written (entries start as the all-ones pattern here)
-    {
-      std::vector<uint32_t> probe(entries);
-      (void)probe;
+    if (hist[nbp + 4]) {
+      // rank mode: the ranks K1 handed out number every bucket's entries 0 .. count-1 exactly once
       std::vector<uint32_t> seen(offsets[p.nb_total], 0);
       for (int j = 0; j < p.nwin; j++)
         for (size_t i = 0; i < n; i++) {
@@ -111,6 +111,9 @@ int emu_accumulate(const Affine<typename G::F>* points, uint32_t row_stride, con
           if (pos >= offsets[b + 1] || seen[pos]++) return 10;
         }
       for (uint32_t v : seen) if (v != 1) return 10;
+    } else {
+      for (size_t i = 0; i < nbp; i++)
+        if (hist[i] != 0) return 10;   // plain mode: every counter must have been consumed exactly by the scatter
     }
     if (o.mode & 2) {
       // K2 (batch-affine, engine_impl.cuh's affine branch): balanced tree over the bucket-ordered entries, one shared

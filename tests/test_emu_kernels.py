@@ -378,11 +378,12 @@ def test_emulated_quad_tail_skewed_and_all_equal():
 
 
 def test_emulated_k1_rank_numbering_paths():
-    """K1 numbers every entry inside its bucket with the returning atomicAdd that counts it (the scatter then needs no
-    atomics).  Three ways through it: plain atomics (random scalars), warp-aggregated atomics forced everywhere (mode bit 4),
-    and the two adaptive triggers -- runs of equal scalars (neighbouring lanes hold equal digits: "redundancy",
-    multiexp_test.go:327-334) and a global hot value found by the sampling pass ("smallvalues", :316-325: every 5th scalar
-    equal).  The emulated engine checks that the ranks of every bucket are a permutation of 0 .. count-1 (rc 10 otherwise)."""
+    """the two modes of the counting sort (kernels.cuh K1 / K1c): plain -- RED histogram, positions from a returning atomicSub in
+    the scatter -- and rank mode -- K1's warp-aggregated returning atomicAdd numbers the entries, the scatter has no atomics.
+    Mode bit 4 forces rank mode, bit 5 plain mode, neither lets the sampling pass decide: it must flag runs of equal scalars
+    ("redundancy", multiexp_test.go:327-334) and a global hot value ("smallvalues", :316-325: every 5th scalar equal).  The
+    emulated engine checks the ranks of every bucket are a permutation of 0 .. count-1, or that the plain scatter consumed
+    every counter exactly (rc 10 otherwise)."""
     g = "bn254_g1"
     pts, s = make_inputs(g, 3000, 13, specials=False)
     small = s.copy()
@@ -392,6 +393,6 @@ def test_emulated_k1_rank_numbering_paths():
         red[i : i + 100] = red[i]
     for scal in (s, small, red):
         want, _, _, _ = cref.msm(g, pts, scal, c=0, nthreads=4)
-        for mode in (0, 16):
+        for mode in (0, 16, 32):
             _check(g, emu_msm(g, pts, scal, 9, K=8, mode=mode), want)
             _check(g, emu_msm(g, pts, scal, 6, tables=1, K=8, passes=2, mode=mode), want)

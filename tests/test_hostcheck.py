@@ -21,14 +21,15 @@ _LIBS = {}
 def _build(variant):
     """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
     if variant not in _LIBS:
-        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr"}[variant]
+        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot"}[variant]
         out = OUT % tag
         bdir = os.path.dirname(out)
         os.makedirs(bdir, exist_ok=True)
         srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h", ".cpp"))]
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in srcs):
             flags = ["-std=c++17", "-O1", "-fPIC"] + {"portable": [], "emulated": ["-DGMSM_EMULATE_PTX"],
-                                                     "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"]}[variant]
+                                                     "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"],
+                                                     "emulated_fp2dot": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
             for k in list(range(6)) + [None]:
@@ -43,7 +44,8 @@ def _build(variant):
 
 # "emulated_sqr": the experimental dedicated squaring and fused two-product routine of field.cuh
 # (-DGMSM_SQR_DEDICATED=1 -DGMSM_DOT2=1, not in the default build); the point formulas of curve.cuh then use them
-@pytest.fixture(scope="module", params=["portable", "emulated", "emulated_sqr"])
+# "emulated_fp2dot": additionally the Fp2 product as two fused two-product reductions (fp2.cuh, -DGMSM_FP2_DOT2=1)
+@pytest.fixture(scope="module", params=["portable", "emulated", "emulated_sqr", "emulated_fp2dot"])
 def hc(request):
     return _build(request.param)
 
