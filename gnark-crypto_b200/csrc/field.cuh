@@ -342,8 +342,13 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
 // 35 .. 100+ KB of straight-line code against a 32 KB L1.5 instruction cache.  GMSM_MUL_NOINLINE trades a
 // CALL/RET pair per multiplication for an instruction footprint that fits.
 #if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P> GMSM_HD Fp<P> fp_mul_karatsuba(const Fp<P>& x, const Fp<P>& y);
 template <class P>
 __device__ __noinline__ Fp<P> fp_mul_ni(Fp<P> x, Fp<P> y) {
+#if defined(GMSM_MUL_KARATSUBA)
+  if constexpr (P::N % 4 == 0 && (P::mod(P::N - 1) >> 30) == 0) return fp_mul_karatsuba(x, y);
+  else
+#endif
   return fp_mul_inline(x, y);
 }
 template <class P>
@@ -351,8 +356,13 @@ GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
   return fp_mul_ni<P>(x, y);
 }
 #else
+template <class P> GMSM_HD Fp<P> fp_mul_karatsuba(const Fp<P>& x, const Fp<P>& y);   // (defined with the separated routines below)
 template <class P>
 GMSM_HD Fp<P> fp_mul(const Fp<P>& x, const Fp<P>& y) {
+#if defined(GMSM_MUL_KARATSUBA)
+  if constexpr (P::N % 4 == 0 && (P::mod(P::N - 1) >> 30) == 0) return fp_mul_karatsuba(x, y);
+  else
+#endif
   return fp_mul_inline(x, y);
 }
 #endif
@@ -585,6 +595,251 @@ GMSM_HD Fp<P> fp_dot2(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P
   {
     return fp_add(fp_mul(x, y), fp_mul(u, v));
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Separated product / reduction (experimental building blocks: -DGMSM_FP2_LAZY=1 uses them for the Fp2 product)
+//   fp_mul_wide : t[0..2N) = x * y, plain 2N-limb product (operands are any N-limb integers)
+//   fp_redc_wide: T * R^-1 mod q for a 2N-limb T < ~3 q R  =  redc_half(T_lo) + T_hi, where redc_half(v) = (v + m q) / R is the
+//                 reduction half of the CIOS above (fp_mul_inline with y = 1: same frames, same carry injection, the product
+//                 MADs dropped: N^2 + N IMAD.WIDE)
+// Same IMAD.WIDE count as the interleaved CIOS (N^2 + N^2 + N), but sums / differences of several double-width products can
+// share ONE reduction (lazy reduction: the Fp2 product of e2_bn254.go:28-38 needs 3 products and 2 reductions, 336 instead of
+// 3 x 136 = 408 IMAD.WIDE for N = 8).
+// ------------------------------------------------------------------------------------------
+template <int N>
+GMSM_HD void mul_wide_limbs(const uint32_t* x, const uint32_t* y, uint32_t* t) {
+  static_assert(N % 2 == 0, "even limb count");
+#if defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+  // two accumulators of 64-bit-aligned (lo, hi) pairs: E holds the pairs at even limb positions, O at odd ones; the product
+  // x_j * y_i sits at position i + j.  Every chain covers N contiguous limbs and drops its carry into the next, still small, limb.
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+  for (int i = 0; i < 2 * N + 2; i++) E[i] = O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Pe = (i & 1) ? O : E;   // x_even * y_i: positions of the parity of i
+    uint32_t* Po = (i & 1) ? E : O;   // x_odd  * y_i: the other parity
+    const uint32_t bi = y[i];
+    Pe[i] = mad_lo_cc(x[0], bi, Pe[i]);
+    Pe[i + 1] = madc_hi_cc(x[0], bi, Pe[i + 1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Pe[i + j] = madc_lo_cc(x[j], bi, Pe[i + j]);
+      Pe[i + j + 1] = madc_hi_cc(x[j], bi, Pe[i + j + 1]);
+    }
+    Pe[i + N] = addc(Pe[i + N], 0);
+    Po[i + 1] = mad_lo_cc(x[1], bi, Po[i + 1]);
+    Po[i + 2] = madc_hi_cc(x[1], bi, Po[i + 2]);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+      Po[i + j] = madc_lo_cc(x[j], bi, Po[i + j]);
+      Po[i + j + 1] = madc_hi_cc(x[j], bi, Po[i + j + 1]);
+    }
+    Po[i + N + 1] = addc(Po[i + N + 1], 0);
+  }
+  t[0] = add_cc(E[0], O[0]);
+#pragma unroll
+  for (int i = 1; i < 2 * N - 1; i++) t[i] = addc_cc(E[i], O[i]);
+  t[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 1]);
+#else
+  for (int i = 0; i < 2 * N; i++) t[i] = 0;
+  for (int i = 0; i < N; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < N; j++) {
+      c += (uint64_t)x[j] * y[i] + t[i + j];
+      t[i + j] = (uint32_t)c;
+      c >>= 32;
+    }
+    t[i + N] = (uint32_t)c;
+  }
+#endif
+}
+
+template <class P>
+GMSM_HD void fp_mul_wide(const uint32_t* x, const uint32_t* y, uint32_t* t) {
+  mul_wide_limbs<P::N>(x, y, t);
+}
+
+// One level of Karatsuba on top of the plain product (N = 2H, H even): x = xl + xh B, y = yl + yh B with B = 2^(32H),
+//   x y = z0 + (zm - z0 - z2) B + z2 B^2,  z0 = xl yl, z2 = xh yh, zm = (xl + xh)(yl + yh)
+// three H x H products (3 H^2 = 48 IMAD.WIDE for N = 8 instead of 64) for ~60 more additions; the carry bits of the two
+// half sums are handled with masked additions.
+template <int N>
+GMSM_HD void mul_wide_karatsuba(const uint32_t* x, const uint32_t* y, uint32_t* t) {
+  constexpr int H = N / 2;
+  static_assert(H % 2 == 0, "N must be a multiple of 4");
+  uint32_t sx[H], sy[H], zm[2 * H + 1];
+  uint32_t cx, cy;
+#if defined(GMSM_PTX_PATH)
+  sx[0] = add_cc(x[0], x[H]);
+#pragma unroll
+  for (int i = 1; i < H; i++) sx[i] = addc_cc(x[i], x[H + i]);
+  cx = addc(0, 0);
+  sy[0] = add_cc(y[0], y[H]);
+#pragma unroll
+  for (int i = 1; i < H; i++) sy[i] = addc_cc(y[i], y[H + i]);
+  cy = addc(0, 0);
+#else
+  { uint64_t c = 0; for (int i = 0; i < H; i++) { c += (uint64_t)x[i] + x[H + i]; sx[i] = (uint32_t)c; c >>= 32; } cx = (uint32_t)c; }
+  { uint64_t c = 0; for (int i = 0; i < H; i++) { c += (uint64_t)y[i] + y[H + i]; sy[i] = (uint32_t)c; c >>= 32; } cy = (uint32_t)c; }
+#endif
+  mul_wide_limbs<H>(x, y, t);                  // z0 -> t[0 .. 2H)
+  mul_wide_limbs<H>(x + H, y + H, t + 2 * H);  // z2 -> t[2H .. 4H)
+  mul_wide_limbs<H>(sx, sy, zm);
+  zm[2 * H] = cx & cy;
+  const uint32_t mx = 0u - cx, my = 0u - cy;   // all ones if the half sum carried
+#if defined(GMSM_PTX_PATH)
+  // zm += (cx ? sy : 0) B + (cy ? sx : 0) B      (into limbs H .. 2H, carries into zm[2H])
+  zm[H] = add_cc(zm[H], sy[0] & mx);
+#pragma unroll
+  for (int i = 1; i < H; i++) zm[H + i] = addc_cc(zm[H + i], sy[i] & mx);
+  zm[2 * H] = addc(zm[2 * H], 0);
+  zm[H] = add_cc(zm[H], sx[0] & my);
+#pragma unroll
+  for (int i = 1; i < H; i++) zm[H + i] = addc_cc(zm[H + i], sx[i] & my);
+  zm[2 * H] = addc(zm[2 * H], 0);
+  // zm -= z0; zm -= z2    (the middle term is non-negative: no borrow out of limb 2H)
+  zm[0] = sub_cc(zm[0], t[0]);
+#pragma unroll
+  for (int i = 1; i < 2 * H; i++) zm[i] = subc_cc(zm[i], t[i]);
+  zm[2 * H] = subc(zm[2 * H], 0);
+  zm[0] = sub_cc(zm[0], t[2 * H]);
+#pragma unroll
+  for (int i = 1; i < 2 * H; i++) zm[i] = subc_cc(zm[i], t[2 * H + i]);
+  zm[2 * H] = subc(zm[2 * H], 0);
+  // t += zm B
+  t[H] = add_cc(t[H], zm[0]);
+#pragma unroll
+  for (int i = 1; i <= 2 * H; i++) t[H + i] = addc_cc(t[H + i], zm[i]);
+#pragma unroll
+  for (int i = 3 * H + 1; i < 4 * H - 1; i++) t[i] = addc_cc(t[i], 0);
+  t[4 * H - 1] = addc(t[4 * H - 1], 0);
+#else
+  { uint64_t c = 0; for (int i = 0; i < H; i++) { c += (uint64_t)zm[H + i] + (sy[i] & mx); zm[H + i] = (uint32_t)c; c >>= 32; } zm[2 * H] += (uint32_t)c; }
+  { uint64_t c = 0; for (int i = 0; i < H; i++) { c += (uint64_t)zm[H + i] + (sx[i] & my); zm[H + i] = (uint32_t)c; c >>= 32; } zm[2 * H] += (uint32_t)c; }
+  { uint64_t br = 0; for (int i = 0; i < 2 * H; i++) { uint64_t d = (uint64_t)zm[i] - t[i] - br; zm[i] = (uint32_t)d; br = (d >> 32) & 1; } zm[2 * H] -= (uint32_t)br; }
+  { uint64_t br = 0; for (int i = 0; i < 2 * H; i++) { uint64_t d = (uint64_t)zm[i] - t[2 * H + i] - br; zm[i] = (uint32_t)d; br = (d >> 32) & 1; } zm[2 * H] -= (uint32_t)br; }
+  { uint64_t c = 0; for (int i = 0; i <= 2 * H; i++) { c += (uint64_t)t[H + i] + zm[i]; t[H + i] = (uint32_t)c; c >>= 32; }
+    for (int i = 3 * H + 1; i < 4 * H; i++) { c += t[i]; t[i] = (uint32_t)c; c >>= 32; } }
+#endif
+}
+
+// (v + m q) / R for an N-limb integer v (any value below 2^(32N)); result < q + 1 limbs-wise NOT reduced: below 2q
+template <class P>
+GMSM_HD void fp_redc_half(const uint32_t* v, uint32_t* out) {
+  constexpr int N = P::N;
+#if defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+  uint32_t A[N + 2], B[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
+  uint32_t dprev = 0, e0prev = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Ev = (i & 1) ? B : A;
+    uint32_t* Od = (i & 1) ? A : B;
+    const uint32_t d = (i == 0) ? 0u : Od[1];
+    if (i == 0) {
+      // row 0 of the CIOS with y_0 = 1: Ev pairs = (v_even, 0), Od pairs = (v_odd, 0)
+#pragma unroll
+      for (int j = 0; j < N; j += 2) { Ev[j] = v[j]; Ev[j + 1] = 0; Od[j] = v[j + 1]; Od[j + 1] = 0; }
+    } else {
+      // later rows add nothing: the row's carry-in ripples through Ev, Od is shifted two limbs
+      (void)add_cc(e0prev, dprev);
+#pragma unroll
+      for (int j = 0; j < N; j++) Ev[j] = addc_cc(Ev[j], 0);
+      Ev[N] = addc(0, 0);
+#pragma unroll
+      for (int j = 0; j < N; j++) Od[j] = Od[j + 2];
+      Od[N] = 0;
+    }
+    const uint32_t m = (Ev[0] + d) * P::INV;
+    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
+    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+    }
+    GMSM_NO_CARRY();
+    e0prev = Ev[0];
+    dprev = d;
+  }
+  (void)add_cc(e0prev, dprev);
+  out[0] = addc_cc(A[0], B[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) out[i] = addc_cc(A[i], B[i + 1]);
+  out[N - 1] = addc(A[N - 1], B[N]);
+#else
+  uint32_t t[N + 2];
+  for (int i = 0; i < N; i++) t[i] = v[i];
+  t[N] = t[N + 1] = 0;
+  for (int i = 0; i < N; i++) {
+    const uint32_t m = t[0] * P::INV;
+    uint64_t c = (uint64_t)m * P::mod(0) + t[0];
+    c >>= 32;
+    for (int j = 1; j < N; j++) {
+      c += (uint64_t)m * P::mod(j) + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[N];
+    t[N - 1] = (uint32_t)c;
+    t[N] = (uint32_t)(c >> 32);
+  }
+  for (int i = 0; i < N; i++) out[i] = t[i];
+#endif
+}
+
+// T * R^-1 mod q, fully reduced, for a 2N-limb T < NRED * q * R (redc_half(T_lo) <= q, T_hi < NRED * q: NRED conditional
+// subtractions; (NRED + 1) q must fit the limbs)
+template <class P, int NRED = 3>
+GMSM_HD Fp<P> fp_redc_wide(const uint32_t* t) {
+  constexpr int N = P::N;
+  uint32_t lo[N];
+  fp_redc_half<P>(t, lo);
+  Fp<P> r;
+#if defined(GMSM_PTX_PATH)
+  r.l[0] = add_cc(lo[0], t[N]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(lo[i], t[N + i]);
+  r.l[N - 1] = addc(lo[N - 1], t[2 * N - 1]);
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < N; i++) {
+    c += (uint64_t)lo[i] + t[N + i];
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < NRED; k++) fp_reduce_once(r);
+  return r;
+}
+
+// x * y = REDC(Karatsuba(x, y)): 3 (N/2)^2 + N^2 + N IMAD.WIDE (120 for N = 8 instead of 136); inputs < q, so T < q^2 and one
+// conditional subtraction suffices
+template <class P>
+GMSM_HD Fp<P> fp_mul_karatsuba(const Fp<P>& x, const Fp<P>& y) {
+  uint32_t t[2 * P::N];
+  mul_wide_karatsuba<P::N>(x.l, y.l, t);
+  return fp_redc_wide<P, 1>(t);
+}
+
+// x * y through the separated routines (for tests: identical values to fp_mul)
+template <class P>
+GMSM_HD Fp<P> fp_mul_split(const Fp<P>& x, const Fp<P>& y) {
+  uint32_t t[2 * P::N];
+  fp_mul_wide<P>(x.l, y.l, t);
+  return fp_redc_wide<P>(t);
 }
 
 // Montgomery -> canonical: multiply by 1 (fromMont, fr/element.go:593-642)

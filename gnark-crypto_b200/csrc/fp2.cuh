@@ -31,6 +31,68 @@ GMSM_HD Fp<P> fp_mul_by5(const Fp<P>& c) {  // fp.MulBy5
   return fp_add(fp_dbl(fp_dbl(c)), c);
 }
 
+#if defined(GMSM_FP2_LAZY)
+// Fp2 product with lazy reduction (beta = -1 only): three double-width products, two reductions -- z1 = (x0+x1)(y0+y1) - x0y0 -
+// x1y1 and z0 = x0y0 - x1y1 + qR are formed on 2N limbs and reduced once each: 3 N^2 + 2 (N^2 + N) = 336 IMAD.WIDE for N = 8
+// against Karatsuba's 3 x 136 = 408.  Same unique reduced values.
+template <class P>
+GMSM_HD Fp2<P> fp2_mul_lazy_inline(const Fp2<P>& x, const Fp2<P>& y) {
+    constexpr int N = P::N;
+    uint32_t sx[N], sy[N], T0[2 * N], T1[2 * N], T2[2 * N];
+#if defined(GMSM_PTX_PATH)
+    sx[0] = add_cc(x.a0.l[0], x.a1.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) sx[i] = addc_cc(x.a0.l[i], x.a1.l[i]);
+    sx[N - 1] = addc(x.a0.l[N - 1], x.a1.l[N - 1]);
+    sy[0] = add_cc(y.a0.l[0], y.a1.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) sy[i] = addc_cc(y.a0.l[i], y.a1.l[i]);
+    sy[N - 1] = addc(y.a0.l[N - 1], y.a1.l[N - 1]);
+#else
+    { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)x.a0.l[i] + x.a1.l[i]; sx[i] = (uint32_t)c; c >>= 32; } }
+    { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)y.a0.l[i] + y.a1.l[i]; sy[i] = (uint32_t)c; c >>= 32; } }
+#endif
+    fp_mul_wide<P>(x.a0.l, y.a0.l, T0);
+    fp_mul_wide<P>(x.a1.l, y.a1.l, T1);
+    fp_mul_wide<P>(sx, sy, T2);
+#if defined(GMSM_PTX_PATH)
+    // T2 -= T0; T2 -= T1   (x0 y1 + x1 y0 >= 0: no borrow out)
+    T2[0] = sub_cc(T2[0], T0[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) T2[i] = subc_cc(T2[i], T0[i]);
+    T2[2 * N - 1] = subc(T2[2 * N - 1], T0[2 * N - 1]);
+    T2[0] = sub_cc(T2[0], T1[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) T2[i] = subc_cc(T2[i], T1[i]);
+    T2[2 * N - 1] = subc(T2[2 * N - 1], T1[2 * N - 1]);
+    // T0 = T0 - T1 + q R  (mod 2^(64N); the true value lies in (qR - q^2, qR + q^2))
+    T0[0] = sub_cc(T0[0], T1[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) T0[i] = subc_cc(T0[i], T1[i]);
+    T0[2 * N - 1] = subc(T0[2 * N - 1], T1[2 * N - 1]);
+    T0[N] = add_cc(T0[N], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) T0[N + i] = addc_cc(T0[N + i], P::mod(i));
+    T0[2 * N - 1] = addc(T0[2 * N - 1], P::mod(N - 1));
+#else
+    { uint64_t br = 0; for (int i = 0; i < 2 * N; i++) { uint64_t d = (uint64_t)T2[i] - T0[i] - br; T2[i] = (uint32_t)d; br = (d >> 32) & 1; } }
+    { uint64_t br = 0; for (int i = 0; i < 2 * N; i++) { uint64_t d = (uint64_t)T2[i] - T1[i] - br; T2[i] = (uint32_t)d; br = (d >> 32) & 1; } }
+    { uint64_t br = 0; for (int i = 0; i < 2 * N; i++) { uint64_t d = (uint64_t)T0[i] - T1[i] - br; T0[i] = (uint32_t)d; br = (d >> 32) & 1; } }
+    { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)T0[N + i] + P::mod(i); T0[N + i] = (uint32_t)c; c >>= 32; } }
+#endif
+    Fp2<P> z;
+    z.a1 = fp_redc_wide<P, 1>(T2);    // < 2 q^2 < q R / 2: redc_half <= q plus T_hi < q / 2
+    z.a0 = fp_redc_wide<P, 2>(T0);    // < q R + q^2:       redc_half <= q plus T_hi < 1.25 q
+    return z;
+}
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp2<P> fp2_mul_lazy_ni(Fp2<P> x, Fp2<P> y) {
+  return fp2_mul_lazy_inline(x, y);
+}
+#endif
+#endif
+
 // Karatsuba, 3 fp.Mul (e2_bn254.go:28-38; e2_bls377.go:12-23 with the a1*b1 term times 5)
 // GMSM_FP2_DOT2 = 1 (experimental): z0 = x0 y0 + x1 (beta y1) and z1 = x0 y1 + x1 y0 as two fused two-product reductions
 // (fp_dot2, field.cuh): 4 products + 2 reductions = 400 IMAD.WIDE for N = 8 against Karatsuba's 3 x 136 = 408, without the
@@ -38,6 +100,15 @@ GMSM_HD Fp<P> fp_mul_by5(const Fp<P>& c) {  // fp.MulBy5
 template <class P>
 GMSM_HD Fp2<P> f_mul(const Fp2<P>& x, const Fp2<P>& y) {
   static_assert(P::FP2_NONRES == -1 || P::FP2_NONRES == -5, "supported quadratic non-residues");
+#if defined(GMSM_FP2_LAZY)
+  if constexpr (P::FP2_NONRES == -1 && (P::mod(P::N - 1) >> 30) == 0) {
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+    return fp2_mul_lazy_ni<P>(x, y);
+#else
+    return fp2_mul_lazy_inline(x, y);
+#endif
+  }
+#endif
 #if defined(GMSM_FP2_DOT2) && defined(GMSM_DOT2)
   Fp2<P> z;
   const Fp<P> by1 = (P::FP2_NONRES == -5) ? fp_neg(fp_mul_by5(y.a1)) : fp_neg(y.a1);

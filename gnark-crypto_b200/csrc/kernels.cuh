@@ -480,6 +480,11 @@ GMSM_D uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t len, ui
 #ifndef GMSM_ACC_TMA
 #define GMSM_ACC_TMA 0
 #endif
+// GMSM_ACC_NOPREFETCH = 1 (experimental): no software pipeline at all -- each iteration loads its own point and relies on the
+// other resident warps to cover the gather latency; frees the registers of the prefetched point without extra instructions.
+#ifndef GMSM_ACC_NOPREFETCH
+#define GMSM_ACC_NOPREFETCH 0
+#endif
 #if GMSM_ACC_TMA && defined(__CUDA_ARCH__)
 GMSM_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 GMSM_D void tma_bar_init(uint32_t bar) {
@@ -566,6 +571,8 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
       e_next = entries[pos + 1];
       tma_load_1d(slot_a, points + (e_next >> 1), (uint32_t)sizeof(Affine<F>), bar_a);
     }
+#elif GMSM_ACC_NOPREFETCH
+    if (has_next) e_next = entries[pos + 1];
 #else
     Affine<F> pt_next;
     if (has_next) {
@@ -603,6 +610,8 @@ k_accumulate(const Affine<typename G::F>* __restrict__ points, const uint32_t* _
       tma_bar_wait(bar_a, tma_phase);
       tma_phase ^= 1u;
       pt = load_vec(&tma_slot[threadIdx.x]);
+#elif GMSM_ACC_NOPREFETCH
+      pt = load_vec_ro(points + (e >> 1));
 #else
       pt = pt_next;
 #endif

@@ -88,3 +88,21 @@ def test_header_is_plain_c99_and_links(tmp_path):
                     "-L", libdir, "-lgmsm", "-L", cuda, "-lcudart", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[:4] == ["64", "192", "192", "32"] and out[4].startswith("gmsm-b200")
+
+
+def test_window_model_choices_are_pinned():
+    """gmsm_choose_window_bits (the fitted width model of gmsm.cu) is pure host arithmetic: pin its choices at
+    the configurations whose sweeps were measured on a B200 (profiles/r02_c_sweep_call3.txt, r02_window_model_validation.md) --
+    every one of them is the measured optimum -- and its monotone behaviour in n"""
+    import importlib
+
+    native = importlib.import_module("gnark-crypto_b200._native")
+    L = native.lib()
+    BN_G1, BN_G2, BLS_G1, BLS_G2, B377_G1 = 0, 1, 2, 3, 4
+    want = {(BN_G1, 16): 15, (BN_G1, 18): 15, (BN_G1, 20): 17, (BN_G1, 22): 17, (BN_G1, 23): 17, (BN_G1, 24): 17, (BN_G1, 26): 20,
+            (BLS_G1, 20): 16, (BLS_G1, 22): 17, (BLS_G1, 24): 19, (BN_G2, 20): 17, (BN_G2, 22): 17, (BLS_G2, 20): 17, (B377_G1, 22): 17}
+    for (curve, logn), c in want.items():
+        assert L.gmsm_choose_window_bits(curve, 1 << logn) == c, (curve, logn)
+    for curve in (BN_G1, BN_G2, BLS_G1, BLS_G2):
+        cs = [L.gmsm_choose_window_bits(curve, 1 << k) for k in range(4, 28)]
+        assert all(2 <= c <= 24 for c in cs) and all(b >= a for a, b in zip(cs, cs[1:])), cs     # wider windows for larger n

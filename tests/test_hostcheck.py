@@ -21,7 +21,7 @@ _LIBS = {}
 def _build(variant):
     """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
     if variant not in _LIBS:
-        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot"}[variant]
+        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot", "emulated_fp2lazy": "_emufp2lazy", "portable_fp2lazy": "_fp2lazy", "emulated_kara": "_emukara", "portable_kara": "_kara"}[variant]
         out = OUT % tag
         bdir = os.path.dirname(out)
         os.makedirs(bdir, exist_ok=True)
@@ -29,7 +29,10 @@ def _build(variant):
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in srcs):
             flags = ["-std=c++17", "-O1", "-fPIC"] + {"portable": [], "emulated": ["-DGMSM_EMULATE_PTX"],
                                                      "emulated_sqr": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"],
-                                                     "emulated_fp2dot": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1"]}[variant]
+                                                     "emulated_fp2dot": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1"],
+                                                     "emulated_fp2lazy": ["-DGMSM_EMULATE_PTX", "-DGMSM_FP2_LAZY=1"], "portable_fp2lazy": ["-DGMSM_FP2_LAZY=1"],
+                                                     "emulated_kara": ["-DGMSM_EMULATE_PTX", "-DGMSM_MUL_KARATSUBA=1", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"],
+                                                     "portable_kara": ["-DGMSM_MUL_KARATSUBA=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
             for k in list(range(6)) + [None]:
@@ -44,8 +47,16 @@ def _build(variant):
 
 # "emulated_sqr": the experimental dedicated squaring and fused two-product routine of field.cuh
 # (-DGMSM_SQR_DEDICATED=1 -DGMSM_DOT2=1, not in the default build); the point formulas of curve.cuh then use them
+# "emulated_kara" / "portable_kara": the field product as REDC(one-level Karatsuba) (-DGMSM_MUL_KARATSUBA=1)
+# "emulated_fp2lazy" / "portable_fp2lazy": the Fp2 product with lazy reduction over the separated wide product / REDC routines (-DGMSM_FP2_LAZY=1)
 # "emulated_fp2dot": additionally the Fp2 product as two fused two-product reductions (fp2.cuh, -DGMSM_FP2_DOT2=1)
-@pytest.fixture(scope="module", params=["portable", "emulated", "emulated_sqr", "emulated_fp2dot"])
+# The variants of routines that are NOT in the shipped build (lazy-reduction Fp2 product, Karatsuba product: measured slower,
+# DESIGN.md section 2) run only with GMSM_TEST_EXPERIMENTAL=1, to keep the CPU suite within a few minutes.
+_VARIANTS = ["portable", "emulated", "emulated_sqr", "emulated_fp2dot"] + (
+    ["emulated_fp2lazy", "portable_fp2lazy", "emulated_kara", "portable_kara"] if os.environ.get("GMSM_TEST_EXPERIMENTAL") else [])
+
+
+@pytest.fixture(scope="module", params=_VARIANTS)
 def hc(request):
     return _build(request.param)
 
