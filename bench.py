@@ -693,12 +693,59 @@ def main():
             if "smallvalues" in name or "redundancy" in name:
                 line["configs"][name]["vs_random_scalars"] = line["configs"][name]["ms_per_step"] / base_ms
         # three concurrent calls (BenchmarkManyMultiExpG1Reference, multiexp_test.go:385-415: three goroutines, each one MultiExp)
+        line["two_in_flight"] = two_in_flight(X, g, 24, min(args.steps, 5))
         if not args.no_e2e:
             line["concurrent3"] = concurrent3(X, native, mx, g, 20)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def two_in_flight(X, g, logn, steps):
+    """throughput with TWO device-resident MultiExp in flight (two engine contexts on two streams, calls issued alternately): the
+    latency-bound tail of one call (carry join, bucket reduction, Horner) overlaps the head and the bucket pass of the next --
+    how a prover that commits to several polynomials would drive the engine.  NOT the headline (`value` times one call at a
+    time); both results are compared with each other and the first with the closed form."""
+    torch = X.torch
+    n = 1 << logn
+    engs = [X.pkg.Engine(g, n, c=0, device=X.local_rank) for _ in range(2)]
+    base = engs[0].generate_multiples(_generator_limbs(g), BASE_MULT, 1).cpu().numpy().view(np.uint64).copy()
+    d_points = engs[0].generate_multiples(base, 1, n)
+    h_s = synth_scalars(n, CURVE_BITS[g], 0x5EED0000 + 2)
+    d_s = engs[0].to_device(h_s)
+    outs = [torch.zeros_like(engs[0]._out) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=X.local_rank) for _ in range(2)]
+    L = importlib.import_module("gnark-crypto_b200._native").lib()
+    import ctypes
+
+    def issue(k):
+        rc = L.gmsm_ctx_msm_device(engs[k]._h, d_points.data_ptr(), d_s.data_ptr(), n, outs[k].data_ptr(), ctypes.c_void_p(streams[k].cuda_stream))
+        if rc != 0:
+            raise RuntimeError("gmsm_ctx_msm_device failed")
+
+    torch.cuda.synchronize()
+    for k in (0, 1, 0, 1):
+        issue(k)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(torch.cuda.current_stream(X.local_rank))
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(X.local_rank))
+    reps = 2 * steps
+    for i in range(reps):
+        issue(i & 1)
+    for st in streams:
+        torch.cuda.current_stream(X.local_rank).wait_stream(st)
+    ev1.record(torch.cuda.current_stream(X.local_rank))
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    a, b = outs[0].cpu().numpy().view(np.uint64), outs[1].cpu().numpy().view(np.uint64)
+    ok = closed_form_check(X, g, a, dot_index_mod(h_s, 1, FR_MOD[CURVE_BITS[g]]))
+    for e in engs:
+        e.close()
+    return {"workload": "%s MultiExp n=2^%d, two calls in flight on two contexts / streams" % (g, logn), "ms_per_msm": ms,
+            "value": n / (ms * 1e-3), "unit": "scalar-muls/s", "results_identical": bool(np.array_equal(a, b)), "closed_form": ok}
 
 
 def concurrent3(X, native, mx, g, logn):

@@ -94,10 +94,10 @@ struct WidthModel {
   double tail_ms[7];      // tail_g(c) for c = 13 .. 19
 };
 static const WidthModel& width_model(int curve) {
-  static const WidthModel bn254_g1 = {0.160, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}};
+  static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}};
   static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
-  static const WidthModel bn254_g2 = {0.599, {7.10, 6.96, 6.35, 6.50, 6.25, 10.2, 13.1}};
-  static const WidthModel bls_g2 = {1.353, {14.2, 13.9, 12.7, 13.0, 12.5, 20.4, 26.2}};
+  static const WidthModel bn254_g2 = {0.529, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
+  static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}};
   switch (curve) {
     case GMSM_BN254_G1: return bn254_g1;
     case GMSM_BLS12381_G1: case GMSM_BLS12377_G1: return bls_g1;

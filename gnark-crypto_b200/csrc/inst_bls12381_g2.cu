@@ -12,7 +12,7 @@
 #ifndef GMSM_ACC_NOPREFETCH
 #define GMSM_ACC_NOPREFETCH 1
 #endif
-#if defined(GMSM_G2_FP2DOT)   /* A/B switch: the bn254 G2 choices for this group too */
+#ifndef GMSM_G2_PLAIN_FP2   /* the fused-product Fp2 multiplication here too: 33.9 -> 32.9 ms (bls12-381 G2 2^20), 41.8 -> 41.2 (bls12-377 G2), profiles/r02_ab_g2x_call8.txt */
 #define GMSM_SQR_DEDICATED 1
 #define GMSM_DOT2 1
 #define GMSM_FP2_DOT2 1
