@@ -580,6 +580,112 @@ __device__ __noinline__ Fp<P> fp_dot2_ni(Fp<P> x, Fp<P> y, Fp<P> u, Fp<P> v) {
 }
 #endif
 #endif
+// Sum of FOUR products with one reduction (GMSM_DOT4, used for the y-coordinate over Fp2: each component of
+// (Q - X3) R - Y1 PPP is four base-field products): z = (x0 y0 + x1 y1 + x2 y2 + x3 y3) R^-1 mod q.  4 N^2 + N^2 + N = 328
+// IMAD.WIDE for N = 8 instead of 2 x 200 for two fused pairs.  Frames stay below 5q, which must fit the limbs
+// (bn254: 5q = 0.945 * 2^256); the result is below (4 q / 2^(32N) + 1) q < 2q.
+#if defined(GMSM_DOT4) && defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+template <class P>
+GMSM_HD Fp<P> fp_dot4_inline(const Fp<P>& x0, const Fp<P>& y0, const Fp<P>& x1, const Fp<P>& y1, const Fp<P>& x2, const Fp<P>& y2,
+                             const Fp<P>& x3, const Fp<P>& y3) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  uint32_t A[N + 2], B[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
+  uint32_t dprev = 0, e0prev = 0;
+  const Fp<P>* xs[4] = {&x0, &x1, &x2, &x3};
+  const Fp<P>* ys[4] = {&y0, &y1, &y2, &y3};
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* Ev = (i & 1) ? B : A;
+    uint32_t* Od = (i & 1) ? A : B;
+    const uint32_t d = (i == 0) ? 0u : Od[1];
+    // step 1: Ev += sum_k x_k,even * y_k[i]  (the row's carry-in rides the first chain)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t bi = ys[k]->l[i];
+      const Fp<P>& x = *xs[k];
+      if (k == 0 && i != 0) {
+        (void)add_cc(e0prev, dprev);
+        Ev[0] = madc_lo_cc(x.l[0], bi, Ev[0]);
+      } else {
+        Ev[0] = mad_lo_cc(x.l[0], bi, Ev[0]);
+      }
+      Ev[1] = madc_hi_cc(x.l[0], bi, Ev[1]);
+#pragma unroll
+      for (int j = 2; j < N; j += 2) {
+        Ev[j] = madc_lo_cc(x.l[j], bi, Ev[j]);
+        Ev[j + 1] = madc_hi_cc(x.l[j], bi, Ev[j + 1]);
+      }
+      if (k == 0) Ev[N] = addc(0, 0); else Ev[N] = addc(Ev[N], 0);
+    }
+    // step 2: Od = (Od >> 2 limbs) + sum_k x_k,odd * y_k[i]   (no carry out of any chain)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t bi = ys[k]->l[i];
+      const Fp<P>& x = *xs[k];
+      if (k == 0) {
+        Od[0] = mad_lo_cc(x.l[1], bi, Od[2]);
+        Od[1] = madc_hi_cc(x.l[1], bi, Od[3]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+          Od[j] = madc_lo_cc(x.l[j + 1], bi, Od[j + 2]);
+          Od[j + 1] = madc_hi_cc(x.l[j + 1], bi, Od[j + 3]);
+        }
+        GMSM_NO_CARRY();
+        Od[N] = 0;
+      } else {
+        Od[0] = mad_lo_cc(x.l[1], bi, Od[0]);
+        Od[1] = madc_hi_cc(x.l[1], bi, Od[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+          Od[j] = madc_lo_cc(x.l[j + 1], bi, Od[j]);
+          Od[j + 1] = madc_hi_cc(x.l[j + 1], bi, Od[j + 1]);
+        }
+        GMSM_NO_CARRY();
+      }
+    }
+    // steps 3-5: the reduction of fp_mul_inline, unchanged
+    const uint32_t m = (Ev[0] + d) * P::INV;
+    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+    }
+    Ev[N] = addc(Ev[N], 0);
+    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
+    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+    }
+    GMSM_NO_CARRY();
+    e0prev = Ev[0];
+    dprev = d;
+  }
+  (void)add_cc(e0prev, dprev);
+  r.l[0] = addc_cc(A[0], B[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(A[i], B[i + 1]);
+  r.l[N - 1] = addc(A[N - 1], B[N]);
+  fp_reduce_once(r);
+  return r;
+}
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+template <class P>
+__device__ __noinline__ Fp<P> fp_dot4_ni(Fp<P> x0, Fp<P> y0, Fp<P> x1, Fp<P> y1, Fp<P> x2, Fp<P> y2, Fp<P> x3, Fp<P> y3) {
+  return fp_dot4_inline(x0, y0, x1, y1, x2, y2, x3, y3);
+}
+#endif
+#endif
+template <class P>
+GMSM_HD Fp<P> fp_dot4(const Fp<P>& x0, const Fp<P>& y0, const Fp<P>& x1, const Fp<P>& y1, const Fp<P>& x2, const Fp<P>& y2,
+                      const Fp<P>& x3, const Fp<P>& y3);
+
 // x*y + u*v: the fused form above where it is compiled in and the modulus has the spare bits, two products otherwise
 template <class P>
 GMSM_HD Fp<P> fp_dot2(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P>& v) {
@@ -594,6 +700,22 @@ GMSM_HD Fp<P> fp_dot2(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, const Fp<P
 #endif
   {
     return fp_add(fp_mul(x, y), fp_mul(u, v));
+  }
+}
+template <class P>
+GMSM_HD Fp<P> fp_dot4(const Fp<P>& x0, const Fp<P>& y0, const Fp<P>& x1, const Fp<P>& y1, const Fp<P>& x2, const Fp<P>& y2,
+                      const Fp<P>& x3, const Fp<P>& y3) {
+#if defined(GMSM_DOT4) && defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
+  if constexpr ((P::mod(P::N - 1) >> 30) == 0) {
+#if defined(__CUDA_ARCH__) && defined(GMSM_MUL_NOINLINE)
+    return fp_dot4_ni<P>(x0, y0, x1, y1, x2, y2, x3, y3);
+#else
+    return fp_dot4_inline(x0, y0, x1, y1, x2, y2, x3, y3);
+#endif
+  } else
+#endif
+  {
+    return fp_add(fp_dot2(x0, y0, x1, y1), fp_dot2(x2, y2, x3, y3));
   }
 }
 

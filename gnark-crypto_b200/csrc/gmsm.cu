@@ -507,7 +507,7 @@ class CopyPool {
   };
   CopyPool() {
     int hw = (int)std::thread::hardware_concurrency();
-    nthreads_ = std::max(1, std::min(16, hw / 4));
+    nthreads_ = std::max(1, std::min(32, hw / 4));
     if (const char* e = getenv("GMSM_COPY_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nthreads_ = v; }
     for (int i = 1; i < nthreads_; i++) std::thread([this] { loop(); }).detach();
   }

@@ -20,8 +20,8 @@ def _pkg():
 
 @pytest.fixture(params=["affine", "xyzz"])
 def accumulate_mode(request, monkeypatch):
-    """both bucket-accumulation paths: batch-affine tree (default; multiexp_affine.go's counterpart) and
-    the extended-Jacobian segmented reduction (multiexp_jacobian.go's counterpart)"""
+    """both bucket-accumulation paths: the extended-Jacobian segmented reduction (the engine's default; multiexp_jacobian.go's
+    counterpart) and the batch-affine tree (GMSM_AFFINE=1, off by default; multiexp_affine.go's counterpart)"""
     monkeypatch.setenv("GMSM_AFFINE", "1" if request.param == "affine" else "0")
     return request.param
 

@@ -21,7 +21,7 @@ _LIBS = {}
 def _build(variant):
     """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
     if variant not in _LIBS:
-        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot", "emulated_fp2lazy": "_emufp2lazy", "portable_fp2lazy": "_fp2lazy", "emulated_kara": "_emukara", "portable_kara": "_kara"}[variant]
+        tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot", "emulated_fp2lazy": "_emufp2lazy", "portable_fp2lazy": "_fp2lazy", "emulated_kara": "_emukara", "portable_kara": "_kara", "emulated_dot4": "_emudot4"}[variant]
         out = OUT % tag
         bdir = os.path.dirname(out)
         os.makedirs(bdir, exist_ok=True)
@@ -32,7 +32,8 @@ def _build(variant):
                                                      "emulated_fp2dot": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1"],
                                                      "emulated_fp2lazy": ["-DGMSM_EMULATE_PTX", "-DGMSM_FP2_LAZY=1"], "portable_fp2lazy": ["-DGMSM_FP2_LAZY=1"],
                                                      "emulated_kara": ["-DGMSM_EMULATE_PTX", "-DGMSM_MUL_KARATSUBA=1", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1"],
-                                                     "portable_kara": ["-DGMSM_MUL_KARATSUBA=1"]}[variant]
+                                                     "portable_kara": ["-DGMSM_MUL_KARATSUBA=1"],
+                                                     "emulated_dot4": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1", "-DGMSM_DOT4=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
             for k in list(range(6)) + [None]:
@@ -52,7 +53,7 @@ def _build(variant):
 # "emulated_fp2dot": additionally the Fp2 product as two fused two-product reductions (fp2.cuh, -DGMSM_FP2_DOT2=1)
 # The variants of routines that are NOT in the shipped build (lazy-reduction Fp2 product, Karatsuba product: measured slower,
 # DESIGN.md section 2) run only with GMSM_TEST_EXPERIMENTAL=1, to keep the CPU suite within a few minutes.
-_VARIANTS = ["portable", "emulated", "emulated_sqr", "emulated_fp2dot"] + (
+_VARIANTS = ["portable", "emulated", "emulated_sqr", "emulated_fp2dot"] + (["emulated_dot4"] if os.environ.get("GMSM_TEST_DOT4") else []) + (
     ["emulated_fp2lazy", "portable_fp2lazy", "emulated_kara", "portable_kara"] if os.environ.get("GMSM_TEST_EXPERIMENTAL") else [])
 
 
