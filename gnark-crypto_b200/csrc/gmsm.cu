@@ -96,7 +96,7 @@ struct WidthModel {
 static const WidthModel& width_model(int curve) {
   static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}};
   static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
-  static const WidthModel bn254_g2 = {0.529, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
+  static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
   static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}};
   switch (curve) {
     case GMSM_BN254_G1: return bn254_g1;
@@ -507,7 +507,7 @@ class CopyPool {
   };
   CopyPool() {
     int hw = (int)std::thread::hardware_concurrency();
-    nthreads_ = std::max(1, std::min(32, hw / 4));
+    nthreads_ = std::max(1, std::min(16, hw / 4));
     if (const char* e = getenv("GMSM_COPY_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nthreads_ = v; }
     for (int i = 1; i < nthreads_; i++) std::thread([this] { loop(); }).detach();
   }

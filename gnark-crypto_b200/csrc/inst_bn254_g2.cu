@@ -21,6 +21,11 @@
 #ifndef GMSM_ACC_NOPREFETCH
 #define GMSM_ACC_NOPREFETCH 1
 #endif
+// the y-coordinate of a point addition as two four-product fused reductions (field.cuh fp_dot4): 40.4 -> 39.3 ms at 2^22
+// (profiles/r02_ab_dot4_call10.txt; the 12-limb G2 groups spill with it and stay on the two-product form)
+#ifndef GMSM_DOT4
+#define GMSM_DOT4 1
+#endif
 #include "engine_impl.cuh"
 namespace gmsm {
 GMSM_INSTANTIATE(bn254_g2, vt_bn254_g2)

@@ -50,10 +50,11 @@ def _build(variant):
 # (-DGMSM_SQR_DEDICATED=1 -DGMSM_DOT2=1, not in the default build); the point formulas of curve.cuh then use them
 # "emulated_kara" / "portable_kara": the field product as REDC(one-level Karatsuba) (-DGMSM_MUL_KARATSUBA=1)
 # "emulated_fp2lazy" / "portable_fp2lazy": the Fp2 product with lazy reduction over the separated wide product / REDC routines (-DGMSM_FP2_LAZY=1)
+# "emulated_dot4": additionally the four-product fused reduction behind the Fp2 y-coordinate (-DGMSM_DOT4=1, shipped for bn254 G2)
 # "emulated_fp2dot": additionally the Fp2 product as two fused two-product reductions (fp2.cuh, -DGMSM_FP2_DOT2=1)
 # The variants of routines that are NOT in the shipped build (lazy-reduction Fp2 product, Karatsuba product: measured slower,
 # DESIGN.md section 2) run only with GMSM_TEST_EXPERIMENTAL=1, to keep the CPU suite within a few minutes.
-_VARIANTS = ["portable", "emulated", "emulated_sqr", "emulated_fp2dot"] + (["emulated_dot4"] if os.environ.get("GMSM_TEST_DOT4") else []) + (
+_VARIANTS = ["portable", "emulated", "emulated_sqr", "emulated_fp2dot", "emulated_dot4"] + (
     ["emulated_fp2lazy", "portable_fp2lazy", "emulated_kara", "portable_kara"] if os.environ.get("GMSM_TEST_EXPERIMENTAL") else [])
 
 
