@@ -3,7 +3,8 @@
 mkdir -p gpurun_out
 T=gpurun_out/r2final
 NG=$(nvidia-smi -L | wc -l); echo "GPUs: $NG"
-( time timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider 2>&1 | tail -5 ) 2>&1 | tee ${T}_pytest.log
+SEL=tests; [ "$NG" -gt 1 ] && SEL=tests/test_gpu_dist.py     # the N-GPU box is charged N x: only the tests that need it
+( time timeout 1500 python -m pytest $SEL -x -q -m gpu -p no:cacheprovider 2>&1 | tail -5 ) 2>&1 | tee ${T}_pytest_n$NG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 if [ "$NG" -eq 1 ]; then
   ( time timeout 1500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 ) > ${T}_reference_n1.json 2> ${T}_reference_n1.err; tail -c 700 ${T}_reference_n1.json; tail -4 ${T}_reference_n1.err
