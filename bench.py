@@ -323,8 +323,8 @@ def measure_resident(X, g, logn_local, steps, warmup, c=0, kind=None, sample_clo
     n_total = n * world
     lo, hi = X.distmod.shard_range(n_total, rank, world)
     bits = CURVE_BITS[g]
-    if c == 0 and world > 1:          # every rank runs the plan of the TOTAL size (dist.window_bits_for_total)
-        c = X.distmod.window_bits_for_total(g, n_total)
+    if c == 0 and world > 1:          # every rank runs ONE plan, that of the largest shard (dist.window_bits_for_total)
+        c = X.distmod.window_bits_for_total(g, n_total, world)
     eng = X.pkg.Engine(g, n, c=c, device=X.local_rank)
     W, cc = eng.nwin, eng.c
     wds = AFF_BYTES[g] // 8

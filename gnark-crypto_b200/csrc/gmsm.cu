@@ -970,7 +970,9 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
   }
   // window-table mode: every shard carries the same table width and returns ONE partial
   const bool tables = jobs[0].sh->pipe.tables;
-  const int c = tables ? jobs[0].sh->pipe.tab_c : choose_c_for(b->curve, ci.fr_bits, n);
+  size_t largest = 0;
+  for (const auto& j : jobs) largest = std::max(largest, (size_t)(j.e - j.a));
+  const int c = tables ? jobs[0].sh->pipe.tab_c : choose_c_for(b->curve, ci.fr_bits, largest);   // the plan of the largest shard, on all of them
   const WindowPlan plan = make_plan(ci.fr_bits, c);
   const size_t npart = tables ? 1 : (size_t)plan.nwin;
   std::vector<unsigned char> h_part(jobs.size() * npart * xb);
@@ -1139,7 +1141,8 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
     return pipeline_run(lease.S->pipe, lease.S->d_points, points, scalars, n, out_jac);
   }
   // ---- multi-device: contiguous shards (the reference's recursive halving, multiexp.go:128-140) ----
-  const int c = choose_c_for(curve, ci.fr_bits, n);
+  // one plan for every shard (their partials are added window by window), sized for the work ONE device does: the largest shard
+  const int c = choose_c_for(curve, ci.fr_bits, (n + D - 1) / D);
   const WindowPlan plan = make_plan(ci.fr_bits, c);
   const size_t xb = 16u * ci.coord_words;
   std::vector<unsigned char> h_part(D * plan.nwin * xb);

@@ -34,19 +34,21 @@ def gather_partials(local, world: int, group=None):
     return out
 
 
-def window_bits_for_total(curve: str, n_total: int) -> int:
-    """the window width every rank of a sharded MSM must use: derived ONCE from the total size (gmsm_choose_window_bits), never
-    from a rank's own shard -- uneven shards would otherwise pick different plans and their partials could not be added"""
+def window_bits_for_total(curve: str, n_total: int, world: int = 1) -> int:
+    """the window width every rank of a sharded MSM must use: derived ONCE from (total size, world) -- the width model
+    (gmsm_choose_window_bits) prices the work of one device, so it is asked for the LARGEST shard, ceil(n_total / world) -- and
+    never from a rank's own shard: uneven shards would otherwise pick different plans and their partials could not be added"""
     from . import _native
     from .multiexp import CURVES
 
-    return int(_native.lib().gmsm_choose_window_bits(CURVES[curve], int(n_total)))
+    world = max(1, int(world))
+    return int(_native.lib().gmsm_choose_window_bits(CURVES[curve], (int(n_total) + world - 1) // world))
 
 
 class ShardedMultiExp:
     """engine + process group.  msm() returns the Jacobian triple (device tensor) on every rank.  All ranks must run the same
     window plan: the constructor all-gathers (c, W) and refuses a mismatch (create the engines with
-    c = window_bits_for_total(curve, n_total))."""
+    c = window_bits_for_total(curve, n_total, world))."""
 
     def __init__(self, engine, group=None):
         import torch
@@ -62,7 +64,7 @@ class ShardedMultiExp:
             plans = gather_partials(mine, self.world, group).cpu().view(self.world, 2)
             if not bool((plans == plans[0]).all()):
                 raise ValueError("ranks run different window plans (c, W): %s -- create every engine with "
-                                 "c = window_bits_for_total(curve, n_total)" % plans.tolist())
+                                 "c = window_bits_for_total(curve, n_total, world)" % plans.tolist())
 
     def msm_from_host(self, h_points, h_scalars, n_local: int, d_points_buf, d_scalars_buf, chunks: int = 4):
         """End-to-end sharded MSM from pinned host shards: the shard is cut into `chunks` batches; batch k+1

@@ -108,3 +108,19 @@ def test_sharded_ranks_must_share_one_window_plan(plans, ok):
         assert p.exitcode == 0
     for _, msg in res:
         assert (msg == "ok") if ok else ("different window plans" in msg)
+
+
+def test_window_plan_of_a_sharded_call_is_that_of_the_largest_shard():
+    """dist.window_bits_for_total: one width for every rank, from (total, world) alone -- the model's choice for ceil(n / world)
+    points, whatever the rank's own (possibly smaller) shard is"""
+    import importlib
+
+    distmod = importlib.import_module("gnark-crypto_b200.dist")
+    L = importlib.import_module("gnark-crypto_b200._native").lib()
+    for n_total, world in [(1 << 26, 4), (1 << 26, 8), ((1 << 24) + 5, 3), (1000, 2), (7, 8)]:
+        want = L.gmsm_choose_window_bits(0, (n_total + world - 1) // world)
+        assert distmod.window_bits_for_total("bn254_g1", n_total, world) == want
+        lo, hi = distmod.shard_range(n_total, world - 1, world)
+        assert hi - lo <= (n_total + world - 1) // world
+    assert distmod.window_bits_for_total("bn254_g1", 1 << 26, 4) == L.gmsm_choose_window_bits(0, 1 << 24)
+    assert distmod.window_bits_for_total("bn254_g1", 1 << 20) == L.gmsm_choose_window_bits(0, 1 << 20)
