@@ -36,9 +36,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CURVE_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255, "bls12377_g1": 253, "bls12377_g2": 253}
-AFF_BYTES = {"bn254_g1": 64, "bn254_g2": 128, "bls12381_g1": 96, "bls12381_g2": 192, "bls12377_g1": 96, "bls12377_g2": 192}
+CURVE_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255, "bls12377_g1": 253, "bls12377_g2": 253,
+              "secp256k1_g1": 256, "bw6761_g1": 377, "bw6761_g2": 377}
+AFF_BYTES = {"bn254_g1": 64, "bn254_g2": 128, "bls12381_g1": 96, "bls12381_g2": 192, "bls12377_g1": 96, "bls12377_g2": 192,
+             "secp256k1_g1": 64, "bw6761_g1": 192, "bw6761_g2": 192}
+FP2_GROUPS = ("bn254_g2", "bls12381_g2", "bls12377_g2")       # coordinates in Fp2 (G2 of bw6-761 is over Fp)
 FR_MOD = {
+    256: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+    377: 0x1AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001,
     254: 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
     255: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
     253: 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001,
@@ -54,21 +59,27 @@ def ncores():
         return os.cpu_count() or 1
 
 
+def scalar_words(bits):
+    """fr.Limbs: u64 words of one scalar"""
+    return (bits + 63) // 64
+
+
 def synth_scalars(n, bits, seed):
-    """n uniform values < r as 4 x u64 limbs (mask top limb to fr.Bits, rejection-sample), read as
+    """n uniform values < r as fr.Limbs x u64 limbs (mask top limb to fr.Bits, rejection-sample), read as
     the Montgomery representation -- the analogue of fr.SetRandom (fr/element.go:302-343)."""
     rng = np.random.default_rng(seed)
     q = FR_MOD[bits]
-    ql = [np.uint64((q >> (64 * i)) & (2**64 - 1)) for i in range(4)]
-    out = np.empty((n, 4), dtype=np.uint64)
+    nw = scalar_words(bits)
+    ql = [np.uint64((q >> (64 * i)) & (2**64 - 1)) for i in range(nw)]
+    out = np.empty((n, nw), dtype=np.uint64)
     todo = np.arange(n)
-    top = np.uint64((1 << (bits - 192)) - 1)
+    top = np.uint64((1 << (bits - 64 * (nw - 1))) - 1)
     while todo.size:
-        v = rng.integers(0, 2**64, size=(todo.size, 4), dtype=np.uint64)
-        v[:, 3] &= top
+        v = rng.integers(0, 2**64, size=(todo.size, nw), dtype=np.uint64)
+        v[:, nw - 1] &= top
         lt = np.zeros(todo.size, dtype=bool)
         eq = np.ones(todo.size, dtype=bool)
-        for k in (3, 2, 1, 0):
+        for k in range(nw - 1, -1, -1):
             lt |= eq & (v[:, k] < ql[k])
             eq &= v[:, k] == ql[k]
         out[todo[lt]] = v[lt]
@@ -92,10 +103,11 @@ def skew_scalars(s, kind):
 
 
 def dot_index_mod(limbs, start, r):
-    """sum_i (start + i) * limbs_i mod r, limbs_i read as a 256-bit little-endian integer (numpy block sums of
+    """sum_i (start + i) * limbs_i mod r, limbs_i read as a little-endian integer of fr.Limbs words (numpy block sums of
     14-bit x 32-bit products, Python integers only for the block totals)."""
     n = limbs.shape[0]
-    halves = np.ascontiguousarray(limbs, dtype=np.uint64).view(np.uint32).reshape(n, 8)
+    nh = 2 * limbs.shape[1]
+    halves = np.ascontiguousarray(limbs, dtype=np.uint64).view(np.uint32).reshape(n, nh)
     total = 0
     SUP, CH = 1 << 20, 1 << 16
     for a in range(0, n, SUP):
@@ -108,7 +120,7 @@ def dot_index_mod(limbs, start, r):
                 continue
             prod = hv * part[:, None]
             sums = np.add.reduceat(prod, np.arange(0, b - a, CH), axis=0)      # each < 2^16 * 2^14 * 2^32 = 2^62
-            for k in range(8):
+            for k in range(nh):
                 total += sum(int(x) for x in sums[:, k]) << (32 * k + shift)
     return total % r
 
@@ -173,8 +185,8 @@ def int_pipe_fraction(g, mixed_adds_per_s, sm_mhz, wide_mads_per_mixed_add=None)
     built kernel really executes (dedicated squaring / fused products lower it).
     Returns {"wide_mads_per_s", "peak", "frac"}, or None if the clock is unknown."""
     try:
-        limbs = AFF_BYTES[g] // (16 if g.endswith("g2") else 8)        # 32-bit limbs of one Fp element
-        fp_muls = 28 if g.endswith("g2") else 10
+        limbs = AFF_BYTES[g] // (16 if g in FP2_GROUPS else 8)        # 32-bit limbs of one Fp element
+        fp_muls = 28 if g in FP2_GROUPS else 10
         per_add = wide_mads_per_mixed_add or fp_muls * (2 * limbs * limbs + limbs)
         peak = 148 * 32 * float(sm_mhz) * 1e6
         ach = float(mixed_adds_per_s) * per_add
@@ -293,17 +305,17 @@ def closed_form_check(X, g, result_jac, local_dot):
     r = FR_MOD[CURVE_BITS[g]]
     dots = [local_dot]
     if X.world > 1:
-        t = torch.tensor([(local_dot >> (32 * k)) & 0xFFFFFFFF for k in range(8)], dtype=torch.int64, device="cuda")
-        allt = torch.empty(8 * X.world, dtype=torch.int64, device="cuda")
+        t = torch.tensor([(local_dot >> (32 * k)) & 0xFFFFFFFF for k in range(12)], dtype=torch.int64, device="cuda")
+        allt = torch.empty(12 * X.world, dtype=torch.int64, device="cuda")
         X.dist.all_gather_into_tensor(allt, t)
-        v = allt.cpu().numpy().reshape(X.world, 8)
-        dots = [sum(int(v[q, k]) << (32 * k) for k in range(8)) for q in range(X.world)]
+        v = allt.cpu().numpy().reshape(X.world, 12)
+        dots = [sum(int(v[q, k]) << (32 * k) for k in range(12)) for q in range(X.world)]
     if X.rank != 0:
         return None
     from oracle import oracle as O      # checker
 
     G = O.GROUPS[g]
-    k = sum(dots) * pow(1 << 256, -1, r) * BASE_MULT % r          # Montgomery limbs -> canonical scalars: * R^-1
+    k = sum(dots) * pow(1 << (64 * scalar_words(CURVE_BITS[g])), -1, r) * BASE_MULT % r          # Montgomery limbs -> canonical scalars: * R^-1
     want = G.encode_affine([G.scalar_mul(G.gen, k)])[0] if k else None
     aw = AFF_BYTES[g] // 8               # u64 words of the affine point (X, Y); the Jacobian triple adds Z
     got = np.asarray(result_jac, dtype=np.uint64)
@@ -479,6 +491,7 @@ def main():
     g = args.curve
     bits = CURVE_BITS[g]
     A = AFF_BYTES[g]
+    SW = scalar_words(bits)          # u64 words per scalar
     wds = A // 8
     # ---- headline configuration ----
     if world == 1:
@@ -506,7 +519,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(g, logn_total, world), "n_total": n_total},
         "engine": {"c": res["c"], "windows": res["windows"], "n_per_gpu": n, "parallelism": "shard%d" % world,
-                   "l2": "inputs %.2f GiB per GPU > 126 MB L2 (no flush needed)" % ((n * (A + 32)) / 2**30)},
+                   "l2": "inputs %.2f GiB per GPU > 126 MB L2 (no flush needed)" % ((n * (A + 8 * SW)) / 2**30)},
         "parity": res["parity"],
         "roofline": res["roofline"],
         "stages_ms": res["stages_ms"],
@@ -557,7 +570,7 @@ def main():
     if not args.no_e2e:
         h_points = torch.empty(n * wds, dtype=torch.int64).pin_memory()
         h_points.copy_(d_points.cpu())
-        h_scal = torch.empty(n * 4, dtype=torch.int64).pin_memory()
+        h_scal = torch.empty(n * SW, dtype=torch.int64).pin_memory()
         h_scal.copy_(torch.from_numpy(h_scalars_np.view(np.int64).reshape(-1)))
         hp, hs = h_points.numpy().view(np.uint64), h_scal.numpy().view(np.uint64)
         jac_words = 3 * wds // 2
@@ -593,14 +606,14 @@ def main():
 
         dt = time_e2e(e2e_step, args.steps)
         line["e2e"] = {"value": n_total / dt, "unit": "scalar-muls/s", "ms_per_step": dt * 1e3,
-                       "h2d_bytes_per_step": n_total * (A + 32), "d2h_bytes_per_step": jac_words * 8 * world, "host_memory": "pinned",
+                       "h2d_bytes_per_step": n_total * (A + 8 * SW), "d2h_bytes_per_step": jac_words * 8 * world, "host_memory": "pinned",
                        "path": "gmsm_multiexp one-shot (points+scalars H2D every call)" if world == 1 else
                                "per rank: gmsm_multiexp_window_sums (pinned host shard, H2D pipelined under the bucket pass) -> NCCL all-gather of W partials -> finalize -> D2H"}
         # the same call on ordinary pageable memory -- what a Go caller's slices are
         pp, ps = np.array(hp, copy=True), np.array(hs, copy=True)
         dtp = time_e2e(lambda: e2e_step(pp, ps), min(args.steps, 5))
         line["e2e_pageable"] = {"value": n_total / dtp, "unit": "scalar-muls/s", "ms_per_step": dtp * 1e3,
-                                "h2d_bytes_per_step": n_total * (A + 32), "d2h_bytes_per_step": jac_words * 8 * world,
+                                "h2d_bytes_per_step": n_total * (A + 8 * SW), "d2h_bytes_per_step": jac_words * 8 * world,
                                 "host_memory": "pageable numpy arrays (not registered by the caller)", "vs_pinned": dtp / dt}
         del pp, ps
         if world == 1:
@@ -608,26 +621,26 @@ def main():
             line["gpu_launches"] += launches_e2e * args.steps
             # resident bases (prover flow: SRS static, scalars per call)
             rb = mx.ResidentBases(g, hp.reshape(n, wds), device=local_rank)
-            rb.MultiExp(hs.reshape(n, 4))
+            rb.MultiExp(hs.reshape(n, SW))
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                rr = rb.MultiExp(hs.reshape(n, 4))
+                rr = rb.MultiExp(hs.reshape(n, SW))
             dtr = (time.perf_counter() - t0) / args.steps
             if not np.array_equal(rr, result_jac):
                 raise SystemExit("bench.py: resident-bases result differs")
             line["e2e_resident_bases"] = {"value": n / dtr, "unit": "scalar-muls/s", "ms_per_step": dtr * 1e3,
-                                          "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": jac_words * 8}
+                                          "h2d_bytes_per_step": n * 8 * SW, "d2h_bytes_per_step": jac_words * 8}
             if not args.no_tables:
                 tc = rb.Precompute(args.table_c)
-                rb.MultiExp(hs.reshape(n, 4))
+                rb.MultiExp(hs.reshape(n, SW))
                 t0 = time.perf_counter()
                 for _ in range(args.steps):
-                    rr = rb.MultiExp(hs.reshape(n, 4))
+                    rr = rb.MultiExp(hs.reshape(n, SW))
                 dtt = (time.perf_counter() - t0) / args.steps
                 if not np.array_equal(rr, result_jac):
                     raise SystemExit("bench.py: resident-bases (window tables) result differs")
                 line["e2e_resident_tables"] = {"value": n / dtt, "unit": "scalar-muls/s", "ms_per_step": dtt * 1e3, "c": tc,
-                                               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": jac_words * 8}
+                                               "h2d_bytes_per_step": n * 8 * SW, "d2h_bytes_per_step": jac_words * 8}
             rb.close()
         del h_points, h_scal
 

@@ -20,7 +20,8 @@ FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-UNITS = ["gmsm.cu", "fft.cu", "decode.cu", "inst_bn254_g1.cu", "inst_bn254_g2.cu", "inst_bls12381_g1.cu", "inst_bls12381_g2.cu", "inst_bls12377_g1.cu", "inst_bls12377_g2.cu"]
+UNITS = ["gmsm.cu", "fft.cu", "decode.cu", "inst_bn254_g1.cu", "inst_bn254_g2.cu", "inst_bls12381_g1.cu", "inst_bls12381_g2.cu", "inst_bls12377_g1.cu", "inst_bls12377_g2.cu",
+         "inst_secp256k1_g1.cu", "inst_bw6761_g1.cu", "inst_bw6761_g2.cu"]
 
 
 def _newest_dep():

@@ -27,6 +27,7 @@ int set_err(int code, const char* fmt, ...);
 struct CurveInfo {
   int coord_words;  // u32 words of one coordinate-field element
   int fr_bits;
+  int scalar_bytes; // one fr.Element: 32 (4 x uint64), 48 for bw6-761 (6 x uint64)
 };
 
 }  // namespace gmsm
@@ -133,6 +134,7 @@ struct GroupVTable {
   int (*batch_scalar_mul)(const void* d_table, const void* d_scalars, size_t n, int c, int nwin, void* d_out, cudaStream_t);
   int (*table_level)(const void* d_in, size_t n, int c, void* d_out, cudaStream_t);   // out[i] = 2^c * in[i]
 };
-extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1, vt_bls12377_g2;
+extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1, vt_bls12377_g2, vt_secp256k1_g1,
+    vt_bw6761_g1, vt_bw6761_g2;
 
 }  // namespace gmsm

@@ -138,9 +138,11 @@ struct Fp {
   GMSM_HD bool operator!=(const Fp& b) const { return !(*this == b); }
 };
 
-// r = (a >= q) ? a - q : a, for a < 2q < 2^(32N)
+// r = (a >= q) ? a - q : a, for a value a + carry * 2^(32N) < 2q.  carry is always 0 for the moduli with a spare top bit
+// (2q < 2^(32N)); the full-width moduli (secp256k1 fp and fr, P::FULL) hand in the carry-out of the addition / the carry limb of
+// the multiplier: a - q then wraps to the right N limbs
 template <class P>
-GMSM_HD void fp_reduce_once(Fp<P>& a) {
+GMSM_HD void fp_reduce_once(Fp<P>& a, uint32_t carry = 0) {
   constexpr int N = P::N;
   uint32_t t[N];
 #if defined(GMSM_PTX_PATH)
@@ -148,6 +150,7 @@ GMSM_HD void fp_reduce_once(Fp<P>& a) {
 #pragma unroll
   for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::mod(i));
   uint32_t borrow = subc(0, 0);  // 0xffffffff if a < q
+  if constexpr (P::FULL) borrow = carry ? 0u : borrow;
 #pragma unroll
   for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
 #else
@@ -157,7 +160,7 @@ GMSM_HD void fp_reduce_once(Fp<P>& a) {
     t[i] = (uint32_t)d;
     br = (d >> 32) & 1;
   }
-  if (!br)
+  if (!br || carry)
     for (int i = 0; i < N; i++) a.l[i] = t[i];
 #endif
 }
@@ -168,10 +171,16 @@ GMSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
   constexpr int N = P::N;
   Fp<P> r;
 #if defined(GMSM_PTX_PATH)
+  uint32_t c = 0;
   r.l[0] = add_cc(a.l[0], b.l[0]);
 #pragma unroll
   for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
-  r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);  // q < 2^(32N-1): no carry out
+  if constexpr (P::FULL) {
+    r.l[N - 1] = addc_cc(a.l[N - 1], b.l[N - 1]);
+    c = addc(0, 0);
+  } else {
+    r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);  // q < 2^(32N-1): no carry out
+  }
 #else
   uint64_t c = 0;
   for (int i = 0; i < N; i++) {
@@ -180,7 +189,7 @@ GMSM_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
     c >>= 32;
   }
 #endif
-  fp_reduce_once(r);
+  fp_reduce_once(r, (uint32_t)c);
   return r;
 }
 
@@ -232,9 +241,51 @@ GMSM_HD Fp<P> fp_neg(const Fp<P>& a) {
 // ------------------------------------------------------------------------------------------
 // Montgomery multiplication  z = x*y*R^-1 mod q   (F1)
 // ------------------------------------------------------------------------------------------
+// Textbook CIOS on 32-bit limbs with the two extra words (_mulGeneric, fp/element.go:470-591, at half the word size): the host
+// build's multiplier and, on the device, the multiplier of the FULL-width moduli -- the even/odd-accumulator form below drops
+// carries that only the spare top bit makes zero (T < 2q < 2^(32N)); here the carry limb t[N] joins the final subtraction.
+template <class P>
+GMSM_HD Fp<P> fp_mul_cios(const Fp<P>& x, const Fp<P>& y) {
+  constexpr int N = P::N;
+  Fp<P> r;
+  uint32_t t[N + 2];
+#pragma unroll
+  for (int i = 0; i < N + 2; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      c += (uint64_t)x.l[j] * y.l[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[N];
+    t[N] = (uint32_t)c;
+    t[N + 1] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * P::INV;
+    c = (uint64_t)m * P::mod(0) + t[0];
+    c >>= 32;
+#pragma unroll
+    for (int j = 1; j < N; j++) {
+      c += (uint64_t)m * P::mod(j) + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[N];
+    t[N - 1] = (uint32_t)c;
+    t[N] = t[N + 1] + (uint32_t)(c >> 32);
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) r.l[i] = t[i];
+  fp_reduce_once(r, t[N]);
+  return r;
+}
+
 template <class P>
 GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   constexpr int N = P::N;
+  if constexpr (P::FULL) return fp_mul_cios(x, y);
   Fp<P> r;
 #if defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
   // Two accumulators, N+2 slots each: [0..N-1] limbs, [N] carry limb, [N+1] always zero.
@@ -306,33 +357,7 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   r.l[N - 1] = addc(A[N - 1], B[N]);
   fp_reduce_once(r);
 #else
-  // portable CIOS on 32-bit limbs (same recurrence as fp/element.go:470-591 at half the word size)
-  uint32_t t[N + 2];
-  for (int i = 0; i < N + 2; i++) t[i] = 0;
-  for (int i = 0; i < N; i++) {
-    uint64_t c = 0;
-    for (int j = 0; j < N; j++) {
-      c += (uint64_t)x.l[j] * y.l[i] + t[j];
-      t[j] = (uint32_t)c;
-      c >>= 32;
-    }
-    c += t[N];
-    t[N] = (uint32_t)c;
-    t[N + 1] = (uint32_t)(c >> 32);
-    uint32_t m = t[0] * P::INV;
-    c = (uint64_t)m * P::mod(0) + t[0];
-    c >>= 32;
-    for (int j = 1; j < N; j++) {
-      c += (uint64_t)m * P::mod(j) + t[j];
-      t[j - 1] = (uint32_t)c;
-      c >>= 32;
-    }
-    c += t[N];
-    t[N - 1] = (uint32_t)c;
-    t[N] = t[N + 1] + (uint32_t)(c >> 32);
-  }
-  for (int i = 0; i < N; i++) r.l[i] = t[i];
-  fp_reduce_once(r);
+  return fp_mul_cios(x, y);
 #endif
   return r;
 }
@@ -1019,7 +1044,7 @@ GMSM_HD Fp<P> fp_inv_fermat(const Fp<P>& x) {
 template <class P>
 GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
   constexpr int N = P::N;
-  static_assert((P::mod(N - 1) >> 31) == 0, "needs a spare top bit");
+  if constexpr (P::FULL) return fp_inv_fermat(x);   // x1 + q does not fit the limbs without a spare top bit
   if (x.is_zero()) return x;
   uint32_t u[N], v[N], x1[N], x2[N];
   for (int i = 0; i < N; i++) { u[i] = x.l[i]; v[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }

@@ -47,18 +47,21 @@ extern "C" const char* gmsm_version(void) { return "gmsm-b200 0.1 (sm_100a)"; }
 // ------------------------------------------------------------------------------------------
 static bool curve_info(int curve, CurveInfo* ci) {
   switch (curve) {
-    case GMSM_BN254_G1: *ci = {bn254_g1::F::N, bn254_fr::BITS}; return true;
-    case GMSM_BN254_G2: *ci = {bn254_g2::F::N, bn254_fr::BITS}; return true;
-    case GMSM_BLS12381_G1: *ci = {bls12381_g1::F::N, bls12381_fr::BITS}; return true;
-    case GMSM_BLS12381_G2: *ci = {bls12381_g2::F::N, bls12381_fr::BITS}; return true;
-    case GMSM_BLS12377_G1: *ci = {bls12377_g1::F::N, bls12377_fr::BITS}; return true;
-    case GMSM_BLS12377_G2: *ci = {bls12377_g2::F::N, bls12377_fr::BITS}; return true;
+    case GMSM_BN254_G1: *ci = {bn254_g1::F::N, bn254_fr::BITS, 4 * bn254_fr::N}; return true;
+    case GMSM_BN254_G2: *ci = {bn254_g2::F::N, bn254_fr::BITS, 4 * bn254_fr::N}; return true;
+    case GMSM_BLS12381_G1: *ci = {bls12381_g1::F::N, bls12381_fr::BITS, 4 * bls12381_fr::N}; return true;
+    case GMSM_BLS12381_G2: *ci = {bls12381_g2::F::N, bls12381_fr::BITS, 4 * bls12381_fr::N}; return true;
+    case GMSM_BLS12377_G1: *ci = {bls12377_g1::F::N, bls12377_fr::BITS, 4 * bls12377_fr::N}; return true;
+    case GMSM_BLS12377_G2: *ci = {bls12377_g2::F::N, bls12377_fr::BITS, 4 * bls12377_fr::N}; return true;
+    case GMSM_SECP256K1_G1: *ci = {secp256k1_g1::F::N, secp256k1_fr::BITS, 4 * secp256k1_fr::N}; return true;
+    case GMSM_BW6761_G1: *ci = {bw6761_g1::F::N, bw6761_fr::BITS, 4 * bw6761_fr::N}; return true;
+    case GMSM_BW6761_G2: *ci = {bw6761_g2::F::N, bw6761_fr::BITS, 4 * bw6761_fr::N}; return true;
   }
   return false;
 }
 
 extern "C" size_t gmsm_affine_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 8u * ci.coord_words : 0; }
-extern "C" size_t gmsm_scalar_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 32u : 0; }
+extern "C" size_t gmsm_scalar_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? (size_t)ci.scalar_bytes : 0; }
 extern "C" size_t gmsm_jac_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 12u * ci.coord_words : 0; }
 extern "C" size_t gmsm_xyzz_bytes(gmsm_curve_t c) { CurveInfo ci; return curve_info(c, &ci) ? 16u * ci.coord_words : 0; }
 
@@ -70,6 +73,9 @@ static const GroupVTable* vtable(int curve) {
     case GMSM_BLS12381_G2: return &vt_bls12381_g2;
     case GMSM_BLS12377_G1: return &vt_bls12377_g1;
     case GMSM_BLS12377_G2: return &vt_bls12377_g2;
+    case GMSM_SECP256K1_G1: return &vt_secp256k1_g1;
+    case GMSM_BW6761_G1: return &vt_bw6761_g1;
+    case GMSM_BW6761_G2: return &vt_bw6761_g2;
   }
   return nullptr;
 }
@@ -98,7 +104,12 @@ static const WidthModel& width_model(int curve) {
   static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
   static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
   static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}};
+  // N4 remainder: fitted from one width sweep each (profiles/r02_n4_new_curves.txt)
+  static const WidthModel secp256k1_g1 = {0.30, {4.6, 4.4, 3.9, 4.0, 4.3, 6.7, 11.3}};
+  static const WidthModel bw6761 = {1.50, {21.0, 21.0, 17.7, 18.4, 23.0, 27.5, 34.0}};
   switch (curve) {
+    case GMSM_SECP256K1_G1: return secp256k1_g1;
+    case GMSM_BW6761_G1: case GMSM_BW6761_G2: return bw6761;
     case GMSM_BN254_G1: return bn254_g1;
     case GMSM_BLS12381_G1: case GMSM_BLS12377_G1: return bls_g1;
     case GMSM_BN254_G2: return bn254_g2;
@@ -130,7 +141,9 @@ static int choose_c_for(int curve, int fr_bits, size_t n) {
   }
   return bc;
 }
-static int curve_of_bits_default(int fr_bits) { return fr_bits == 254 ? GMSM_BN254_G1 : (fr_bits == 255 ? GMSM_BLS12381_G1 : GMSM_BLS12377_G1); }
+static int curve_of_bits_default(int fr_bits) {
+  return fr_bits == 254 ? GMSM_BN254_G1 : fr_bits == 255 ? GMSM_BLS12381_G1 : fr_bits == 256 ? GMSM_SECP256K1_G1 : fr_bits == 377 ? GMSM_BW6761_G1 : GMSM_BLS12377_G1;
+}
 static int choose_c(int fr_bits, size_t n) { return choose_c_for(curve_of_bits_default(fr_bits), fr_bits, n); }
 
 // window width of the window-table mode: one shared bucket set, so the bucket reduction costs 2^(c-1) * ~3.8
@@ -637,6 +650,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
                         uint64_t* out_jac, int c_force = 0, void* h_partials = nullptr) {
   CurveInfo ci;
   curve_info(P.curve, &ci);
+  const size_t sb = (size_t)ci.scalar_bytes;
   const size_t ab = 8u * ci.coord_words, xb = 16u * ci.coord_words, jb = 12u * ci.coord_words;
   CK(cudaSetDevice(P.device));
   // batch sizes grow geometrically (1/16, 1/8, 3/16, 1/4, 3/8 of n): the first copy is short, and since the
@@ -678,7 +692,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   for (int k = 0; k < nch; k++) nc = std::max(nc, bstart[k + 1] - bstart[k]);
   if (P.scal_cap < n || P.scal_cap > 4 * n + 1024) {
     cudaFree(P.d_scalars); P.d_scalars = nullptr; P.scal_cap = 0;
-    CK(cudaMalloc(&P.d_scalars, n * 32));
+    CK(cudaMalloc(&P.d_scalars, n * (size_t)ci.scalar_bytes));
     P.scal_cap = n;
   }
   // window width from the TOTAL size (all batches share one bucket array); workspace sized for one batch
@@ -720,7 +734,7 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   // pageable caller buffers go through the pinned ring (GMSM_STAGING=0: hand them to cudaMemcpyAsync as they are)
   bool staging = true;
   if (const char* e = getenv("GMSM_STAGING")) staging = atoi(e) != 0;
-  const bool stage_scalars = staging && n * 32 >= (1u << 20) && !host_pointer_is_pinned(hs);
+  const bool stage_scalars = staging && n * (size_t)ci.scalar_bytes >= (1u << 20) && !host_pointer_is_pinned(hs);
   const bool stage_points = staging && hp && n * ab >= (1u << 20) && !host_pointer_is_pinned(hp);
   P.last_staged = (stage_scalars || stage_points) ? 1 : 0;
   auto h2d = [&](void* dst, const char* src, size_t bytes, bool staged) -> int {
@@ -733,15 +747,15 @@ static int pipeline_run(Pipeline& P, void* d_points, const uint64_t* h_points, c
   for (int k = 0; k < nch; k++) {
     const size_t off = bstart[k];
     const size_t m = bstart[k + 1] - off;
-    if (int rc = h2d((char*)P.d_scalars + off * 32, hs + off * 32, m * 32, stage_scalars)) return rc;
+    if (int rc = h2d((char*)P.d_scalars + off * sb, hs + off * sb, m * sb, stage_scalars)) return rc;
     if (hp) if (int rc = h2d((char*)d_points + off * ab, hp + off * ab, m * ab, stage_points)) return rc;
     CK(cudaEventRecord(P.ev[k], P.copy_st));
     CK(cudaStreamWaitEvent(P.comp_st, P.ev[k], 0));
     int rc;
     if (shared_buckets) {
-      rc = vt->accumulate(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m, k > 0, P.comp_st);
+      rc = vt->accumulate(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * sb, m, k > 0, P.comp_st);
     } else {
-      rc = vt->window_sums(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * 32, m,
+      rc = vt->window_sums(P.ctx, (char*)d_points + off * ab, (char*)P.d_scalars + off * sb, m,
                            (char*)P.d_partials + (size_t)k * npart * xb, P.comp_st);
     }
     if (rc) return rc;
@@ -984,7 +998,7 @@ extern "C" int gmsm_bases_multiexp(gmsm_bases_t* b, size_t offset, const uint64_
       th.emplace_back([&, k]() {
         const Job& j = jobs[k];
         rcs[k] = pipeline_run(j.sh->pipe, reinterpret_cast<char*>(j.sh->d_points) + (j.a - j.sh->lo) * ab, nullptr,
-                              scalars + (j.a - offset) * 4, j.e - j.a, nullptr, c, h_part.data() + k * npart * xb);
+                              scalars + (j.a - offset) * (size_t)(ci.scalar_bytes / 8), j.e - j.a, nullptr, c, h_part.data() + k * npart * xb);
         if (rcs[k]) errs[k] = g_err;
       });
     }
@@ -1160,7 +1174,7 @@ extern "C" int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const u
       th.emplace_back([&, d]() {
         const size_t lo = n * d / D, hi = n * (d + 1) / D;
         Session& S = *leases[d].S;
-        rcs[d] = pipeline_run(S.pipe, S.d_points, points + lo * (ab / 8), scalars + lo * 4, hi - lo, nullptr, c,
+        rcs[d] = pipeline_run(S.pipe, S.d_points, points + lo * (ab / 8), scalars + lo * (size_t)(ci.scalar_bytes / 8), hi - lo, nullptr, c,
                               h_part.data() + d * plan.nwin * xb);
         if (rcs[d]) errs[d] = g_err;   // thread-local error text of the worker
       });
@@ -1184,6 +1198,9 @@ extern "C" int gmsm_bls12381_g1_multiexp(const uint64_t* p, const uint64_t* s, s
 extern "C" int gmsm_bls12381_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BLS12381_G2, p, s, n, t, out); }
 extern "C" int gmsm_bls12377_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[18]) { return gmsm_multiexp(GMSM_BLS12377_G1, p, s, n, t, out); }
 extern "C" int gmsm_bls12377_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BLS12377_G2, p, s, n, t, out); }
+extern "C" int gmsm_secp256k1_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_SECP256K1_G1, p, s, n, t, out); }
+extern "C" int gmsm_bw6761_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BW6761_G1, p, s, n, t, out); }
+extern "C" int gmsm_bw6761_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BW6761_G2, p, s, n, t, out); }
 
 // ------------------------------------------------------------------------------------------
 // base generator
@@ -1234,14 +1251,14 @@ extern "C" int gmsm_batch_scalar_mul(gmsm_curve_t curve, const uint64_t* base_af
   cudaStream_t st = nullptr;
   int rc = GMSM_OK;
   auto cleanup = [&]() { cudaFree(d_table); cudaFree(d_scalars); cudaFree(d_out); if (st) cudaStreamDestroy(st); };
-  if (cudaMalloc(&d_table, tbl * ab) != cudaSuccess || cudaMalloc(&d_scalars, n * 32) != cudaSuccess ||
+  if (cudaMalloc(&d_table, tbl * ab) != cudaSuccess || cudaMalloc(&d_scalars, n * (size_t)ci.scalar_bytes) != cudaSuccess ||
       cudaMalloc(&d_out, n * ab) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
     cleanup();
     return set_err(GMSM_ENOMEM, "gmsm_batch_scalar_mul: device allocation failed");
   }
   rc = gmsm_generate_multiples_device(curve, base_affine, 1, tbl, d_table, st);
   if (rc == GMSM_OK) {
-    cudaError_t ce = cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, st);
+    cudaError_t ce = cudaMemcpyAsync(d_scalars, scalars, n * (size_t)ci.scalar_bytes, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) rc = vtable(curve)->batch_scalar_mul(d_table, d_scalars, n, p.c, p.nwin, d_out, st);
     if (ce == cudaSuccess && rc == GMSM_OK) ce = cudaMemcpyAsync(out_points, d_out, n * ab, cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess && rc == GMSM_OK) ce = cudaStreamSynchronize(st);
@@ -1288,11 +1305,11 @@ extern "C" int gmsm_test_digits(gmsm_curve_t curve, int c, const uint64_t* scala
   if (n == 0) return GMSM_OK;
   WindowPlan p = make_plan(ci.fr_bits, c);
   DevBuf bs, bo;
-  CK(cudaMalloc(&bs.p, n * 32));
+  CK(cudaMalloc(&bs.p, n * (size_t)ci.scalar_bytes));
   CK(cudaMalloc(&bo.p, n * (size_t)p.nwin * 4));
   void* ds = bs.p;
   uint32_t* dout = bo.as<uint32_t>();
-  CK(cudaMemcpy(ds, scalars, n * 32, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ds, scalars, n * (size_t)ci.scalar_bytes, cudaMemcpyHostToDevice));
   if (int rc = vtable(curve)->digits_dump(ds, n, p.c, p.nwin, dout)) return rc;
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, dout, n * (size_t)p.nwin * 4, cudaMemcpyDeviceToHost));

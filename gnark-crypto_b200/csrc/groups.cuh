@@ -32,6 +32,11 @@ using bls12381_g2 = GroupT<3, bls12381_fp, bls12381_fr, true>;
 // next-row N4 (pure parametrisation): bls12-377 G1, ecc/bls12-377/g1.go, fr 253 bits
 using bls12377_g1 = GroupT<4, bls12377_fp, bls12377_fr, false>;
 using bls12377_g2 = GroupT<5, bls12377_fp, bls12377_fr, true>;   // Fp2 with u^2 = -5
+// N4 remainder: secp256k1 (ecc/secp256k1/g1.go; fp and fr fill all 256 bits: Params::FULL, carry-aware field ops),
+// bw6-761 G1 and G2 (ecc/bw6-761/g1.go, g2.go: BOTH over the 12-word Fp; fr = 6 words, 377 bits)
+using secp256k1_g1 = GroupT<6, secp256k1_fp, secp256k1_fr, false>;
+using bw6761_g1 = GroupT<7, bw6761_fp, bw6761_fr, false>;
+using bw6761_g2 = GroupT<8, bw6761_fp, bw6761_fr, false>;
 
 // word (u32) counts
 template <class G> constexpr int coord_words() { return G::F::N; }

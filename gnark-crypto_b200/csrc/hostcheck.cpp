@@ -17,7 +17,7 @@ static int run(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t
   return 0;
 }
 
-// -DHC_GROUP=k compiles one group per translation unit (hostcheck_op_k) so the test can build the six in parallel;
+// -DHC_GROUP=k compiles one group per translation unit (hostcheck_op_k) so the test can build them in parallel;
 // without it this file is the dispatcher + the window plan.
 #if defined(HC_GROUP)
 #define HC_CAT2(a, b) a##b
@@ -32,8 +32,14 @@ using HcG = bls12381_g1;
 using HcG = bls12381_g2;
 #elif HC_GROUP == 4
 using HcG = bls12377_g1;
-#else
+#elif HC_GROUP == 5
 using HcG = bls12377_g2;
+#elif HC_GROUP == 6
+using HcG = secp256k1_g1;
+#elif HC_GROUP == 7
+using HcG = bw6761_g1;
+#else
+using HcG = bw6761_g2;
 #endif
 extern "C" int HC_CAT(hostcheck_op_, HC_GROUP)(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   return run<HcG>(op, a, b, o, n);
@@ -58,54 +64,35 @@ extern "C" int HC_CAT(hostcheck_table_level_, HC_GROUP)(int c, const uint32_t* i
   return 0;
 }
 #else
+#define HC_FOR_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 extern "C" {
-int hostcheck_op_0(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_op_1(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_op_2(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_op_3(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_op_4(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_op_5(int, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-}
-extern "C" {
-int hostcheck_table_level_0(int, const uint32_t*, size_t, uint32_t*);
-int hostcheck_table_level_1(int, const uint32_t*, size_t, uint32_t*);
-int hostcheck_table_level_2(int, const uint32_t*, size_t, uint32_t*);
-int hostcheck_table_level_3(int, const uint32_t*, size_t, uint32_t*);
-int hostcheck_table_level_4(int, const uint32_t*, size_t, uint32_t*);
-int hostcheck_table_level_5(int, const uint32_t*, size_t, uint32_t*);
-}
-extern "C" {
-int hostcheck_dot2_0(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_dot2_2(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
-int hostcheck_dot2_4(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+#define X(k) int hostcheck_op_##k(int, const uint32_t*, const uint32_t*, uint32_t*, size_t); \
+  int hostcheck_table_level_##k(int, const uint32_t*, size_t, uint32_t*); \
+  int hostcheck_dot2_##k(const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t*, size_t);
+HC_FOR_EACH(X)
+#undef X
 }
 extern "C" int hostcheck_dot2(int curve, const uint32_t* x, const uint32_t* y, const uint32_t* u, const uint32_t* v, uint32_t* o, size_t n) {
-  switch (curve) {   // the G1 groups: coordinate field = Fp
-    case 0: return hostcheck_dot2_0(x, y, u, v, o, n);
-    case 2: return hostcheck_dot2_2(x, y, u, v, o, n);
-    case 4: return hostcheck_dot2_4(x, y, u, v, o, n);
+  switch (curve) {   // meaningful for the groups whose coordinate field is Fp (for Fp2 it is the Fp2 sum of products)
+#define X(k) case k: return hostcheck_dot2_##k(x, y, u, v, o, n);
+    HC_FOR_EACH(X)
+#undef X
   }
   return 1;
 }
 extern "C" int hostcheck_table_level(int curve, int c, const uint32_t* in, size_t n, uint32_t* out) {
   switch (curve) {
-    case 0: return hostcheck_table_level_0(c, in, n, out);
-    case 1: return hostcheck_table_level_1(c, in, n, out);
-    case 2: return hostcheck_table_level_2(c, in, n, out);
-    case 3: return hostcheck_table_level_3(c, in, n, out);
-    case 4: return hostcheck_table_level_4(c, in, n, out);
-    case 5: return hostcheck_table_level_5(c, in, n, out);
+#define X(k) case k: return hostcheck_table_level_##k(c, in, n, out);
+    HC_FOR_EACH(X)
+#undef X
   }
   return 1;
 }
 extern "C" int hostcheck_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   switch (curve) {
-    case 0: return hostcheck_op_0(op, a, b, o, n);
-    case 1: return hostcheck_op_1(op, a, b, o, n);
-    case 2: return hostcheck_op_2(op, a, b, o, n);
-    case 3: return hostcheck_op_3(op, a, b, o, n);
-    case 4: return hostcheck_op_4(op, a, b, o, n);
-    case 5: return hostcheck_op_5(op, a, b, o, n);
+#define X(k) case k: return hostcheck_op_##k(op, a, b, o, n);
+    HC_FOR_EACH(X)
+#undef X
   }
   return 1;
 }

@@ -76,18 +76,19 @@ class ShardedMultiExp:
         main = torch.cuda.current_stream(self.engine.device)
         self._copy_stream.wait_stream(main)
         wa = 2 * self.engine.w          # int64 words per affine point
+        ws = self.engine.sw             # int64 words per scalar
         pw = self.engine.partials_bytes // 8
         chunks = max(1, min(chunks, n_local))
         partials = torch.empty(chunks * pw, dtype=torch.int64, device=d_points_buf.device)
         for k in range(chunks):
             lo, hi = n_local * k // chunks, n_local * (k + 1) // chunks
             with torch.cuda.stream(self._copy_stream):
-                d_scalars_buf[lo * 4 : hi * 4].copy_(h_scalars[lo * 4 : hi * 4], non_blocking=True)
+                d_scalars_buf[lo * ws : hi * ws].copy_(h_scalars[lo * ws : hi * ws], non_blocking=True)
                 d_points_buf[lo * wa : hi * wa].copy_(h_points[lo * wa : hi * wa], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             main.wait_event(ev)
-            self.engine.window_sums(d_points_buf[lo * wa :], d_scalars_buf[lo * 4 :], hi - lo, out=partials[k * pw : (k + 1) * pw])
+            self.engine.window_sums(d_points_buf[lo * wa :], d_scalars_buf[lo * ws :], hi - lo, out=partials[k * pw : (k + 1) * pw])
         allp = gather_partials(partials, self.world, self.group)
         return self.engine.finalize(allp, self.world * chunks)
 
@@ -102,7 +103,7 @@ class ShardedMultiExp:
 
         torch = self.engine.torch
         eng = self.engine
-        n_local = h_scalars_np.size // 4
+        n_local = h_scalars_np.size // eng.sw
         part = np.empty(eng.partials_bytes // 8, dtype=np.uint64)
         rc = _native.lib().gmsm_multiexp_window_sums(eng.cid, h_points_np.ctypes.data, h_scalars_np.ctypes.data, n_local, eng.c,
                                                      eng.device, part.ctypes.data)

@@ -22,9 +22,14 @@ import numpy as np
 
 from . import _native
 
-CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5}
+CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5,
+          # N4 remainder: ecc/secp256k1/multiexp.go:32 ; ecc/bw6-761/multiexp.go:32, :306 (G2 of bw6-761 is over Fp too)
+          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8}
 # u64 words: (coordinate limbs L, coordinates per point-coordinate: 1 = Fp, 2 = Fp2)
-_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1), 5: (6, 2)}
+_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1), 5: (6, 2), 6: (4, 1), 7: (12, 1), 8: (12, 1)}
+# fr.Limbs / fr.Bits of each curve id: a scalar is SCALAR_WORDS x uint64 in Montgomery form
+SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6}
+SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377}
 
 
 class MultiExpError(Exception):
@@ -80,7 +85,7 @@ class _JacBase(_Point):
         cid = self.CURVE_ID
         w = _words(cid)
         points = _as_u64(points, 2 * w, "points")
-        scalars = _as_u64(scalars, 4, "scalars")
+        scalars = _as_u64(scalars, SCALAR_WORDS[cid], "scalars")
         if points.shape[0] != scalars.shape[0]:
             raise MultiExpError("len(points) != len(scalars)")  # multiexp.go:61-64
         out = np.zeros(3 * w, dtype=np.uint64)
@@ -136,11 +141,11 @@ class _AffBase(_Point):
 
 
 def curve_package(curve: str):
-    """Returns (G1Affine, G1Jac, G2Affine, G2Jac) bound to `curve` in {"bn254", "bls12381"} -- the
-    analogue of importing ecc/bn254 or ecc/bls12-381."""
+    """Returns (G1Affine, G1Jac, G2Affine, G2Jac) bound to `curve` in {"bn254", "bls12381", "bls12377", "secp256k1", "bw6761"}
+    -- the analogue of importing ecc/bn254, ecc/bls12-381, ... (secp256k1 has no G2: None, None)."""
     out = []
     for grp in ("g1", "g2"):
-        if "%s_%s" % (curve, grp) not in CURVES:   # bls12-377: G1 only
+        if "%s_%s" % (curve, grp) not in CURVES:   # secp256k1: G1 only
             out += [None, None]
             continue
         cid = CURVES["%s_%s" % (curve, grp)]
@@ -170,7 +175,7 @@ class ResidentBases:
 
     def MultiExp(self, scalars, config: MultiExpConfig = None, offset: int = 0):
         config = config or MultiExpConfig()
-        scalars = _as_u64(scalars, 4, "scalars")
+        scalars = _as_u64(scalars, SCALAR_WORDS[self.cid], "scalars")
         out = np.zeros(3 * self.w, dtype=np.uint64)
         rc = _native.lib().gmsm_bases_multiexp(self._h, offset, scalars.ctypes.data, scalars.shape[0], int(config.NbTasks), out.ctypes.data)
         _check(rc)
@@ -181,7 +186,7 @@ class ResidentBases:
         fft.Domain.fft_device): nothing but the 96..288-byte result crosses PCIe"""
         config = config or MultiExpConfig()
         if n is None:
-            n = d_scalars.numel() // 4
+            n = d_scalars.numel() // SCALAR_WORDS[self.cid]
         out = np.zeros(3 * self.w, dtype=np.uint64)
         rc = _native.lib().gmsm_bases_multiexp_device(self._h, offset, d_scalars.data_ptr(), n, int(config.NbTasks), out.ctypes.data, stream)
         _check(rc)
@@ -216,6 +221,7 @@ class Engine:
         self.curve = curve
         self.cid = CURVES[curve]
         self.w = _words(self.cid)
+        self.sw = SCALAR_WORDS[self.cid]       # u64 words per scalar
         self.device = device
         self.tables = tables
         L = _native.lib()
@@ -241,7 +247,7 @@ class Engine:
     def msm(self, d_points, d_scalars, n: int = None):
         """full MSM on device tensors; returns the device tensor holding the Jacobian triple (int64 view)."""
         if n is None:
-            n = d_scalars.numel() // 4
+            n = d_scalars.numel() // self.sw
         rc = _native.lib().gmsm_ctx_msm_device(self._h, d_points.data_ptr(), d_scalars.data_ptr(), n, self._out.data_ptr(), self._stream())
         _check(rc)
         return self._out
@@ -259,7 +265,7 @@ class Engine:
 
     def msm_tables(self, d_table, row_stride: int, d_scalars, n: int = None, offset: int = 0):
         if n is None:
-            n = d_scalars.numel() // 4
+            n = d_scalars.numel() // self.sw
         rc = _native.lib().gmsm_ctx_msm_tables_device(self._h, d_table.data_ptr(), row_stride, offset, d_scalars.data_ptr(), n,
                                                       self._out.data_ptr(), self._stream())
         _check(rc)
@@ -270,7 +276,7 @@ class Engine:
 
     def window_sums(self, d_points, d_scalars, n: int = None, out=None):
         if n is None:
-            n = d_scalars.numel() // 4
+            n = d_scalars.numel() // self.sw
         out = self._partials if out is None else out
         rc = _native.lib().gmsm_ctx_window_sums_device(self._h, d_points.data_ptr(), d_scalars.data_ptr(), n, out.data_ptr(), self._stream())
         _check(rc)
@@ -320,7 +326,7 @@ def BatchScalarMultiplication(curve: str, base, scalars) -> np.ndarray:
     cid = CURVES[curve]
     w = _words(cid)
     base = np.ascontiguousarray(base, dtype=np.uint64).reshape(2 * w)
-    scalars = _as_u64(scalars, 4, "scalars")
+    scalars = _as_u64(scalars, SCALAR_WORDS[cid], "scalars")
     out = np.zeros((scalars.shape[0], 2 * w), dtype=np.uint64)
     rc = _native.lib().gmsm_batch_scalar_mul(cid, base.ctypes.data, scalars.ctypes.data, scalars.shape[0], out.ctypes.data)
     _check(rc)
@@ -339,9 +345,9 @@ def test_op(curve: str, op: int, a: np.ndarray, b: np.ndarray, out_words: int) -
 
 
 def test_digits(curve: str, c: int, scalars: np.ndarray) -> np.ndarray:
-    scalars = _as_u64(scalars, 4, "scalars")
+    scalars = _as_u64(scalars, SCALAR_WORDS[CURVES[curve]], "scalars")
     n = scalars.shape[0]
-    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253}[CURVES[curve]]
+    bits = SCALAR_BITS[CURVES[curve]]
     W = (bits + c - 1) // c
     out = np.zeros((W, n), dtype=np.uint32)
     rc = _native.lib().gmsm_test_digits(CURVES[curve], c, scalars.ctypes.data, n, out.ctypes.data)

@@ -12,8 +12,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libmsmref.so")
 
-CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5}
-AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12, 5: 24}  # u64 words per affine point
+CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5,
+          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8}
+AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12, 5: 24, 6: 8, 7: 24, 8: 24}  # u64 words per affine point
+SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6}      # u64 words per scalar (fr.Limbs)
+SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377}   # fr.Bits
 
 _lib = None
 
@@ -59,7 +62,7 @@ def msm(curve, points: np.ndarray, scalars: np.ndarray, c: int = 0, nthreads: in
     cid = _cid(curve)
     w = AFF_WORDS[cid]
     points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, w)
-    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, SCALAR_WORDS[cid])
     n = points.shape[0]
     assert scalars.shape[0] == n
     aff = np.zeros(w, dtype=np.uint64)
@@ -73,9 +76,9 @@ def msm(curve, points: np.ndarray, scalars: np.ndarray, c: int = 0, nthreads: in
 
 def partition_scalars(curve, scalars: np.ndarray, c: int) -> np.ndarray:
     cid = _cid(curve)
-    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, SCALAR_WORDS[cid])
     n = scalars.shape[0]
-    bits = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253}[cid]
+    bits = SCALAR_BITS[cid]
     W = (bits + c - 1) // c
     out = np.zeros((W, n), dtype=np.uint32)
     rc = lib().ref_partition_scalars(cid, _p(scalars), n, c, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
@@ -99,7 +102,7 @@ def scalar_mul(curve, base_aff: np.ndarray, k: int) -> np.ndarray:
     cid = _cid(curve)
     w = AFF_WORDS[cid]
     base_aff = np.ascontiguousarray(base_aff, dtype=np.uint64).reshape(w)
-    kl = np.array([(k >> (64 * i)) & (2**64 - 1) for i in range(4)], dtype=np.uint64)
+    kl = np.array([(k >> (64 * i)) & (2**64 - 1) for i in range(SCALAR_WORDS[cid])], dtype=np.uint64)
     out = np.zeros(w, dtype=np.uint64)
     rc = lib().ref_scalar_mul(cid, _p(base_aff), _p(kl), _p(out))
     if rc != 0:
@@ -110,17 +113,18 @@ def scalar_mul(curve, base_aff: np.ndarray, k: int) -> np.ndarray:
 def dot_index(curve, scalars: np.ndarray, start: int) -> int:
     """sum_i (start+i) * s_i mod r as a Python int"""
     cid = _cid(curve)
-    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
-    out = np.zeros(4, dtype=np.uint64)
+    sw = SCALAR_WORDS[cid]
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, sw)
+    out = np.zeros(sw, dtype=np.uint64)
     rc = lib().ref_dot_index(cid, _p(scalars), scalars.shape[0], start, _p(out))
     if rc != 0:
         raise RuntimeError("ref_dot_index rc=%d" % rc)
-    return sum(int(out[i]) << (64 * i) for i in range(4))
+    return sum(int(out[i]) << (64 * i) for i in range(sw))
 
 
 def random_scalars(curve, n: int, seed: int) -> np.ndarray:
     cid = _cid(curve)
-    out = np.zeros((n, 4), dtype=np.uint64)
+    out = np.zeros((n, SCALAR_WORDS[cid]), dtype=np.uint64)
     rc = lib().ref_random_scalars(cid, n, seed, _p(out))
     if rc != 0:
         raise RuntimeError("ref_random_scalars rc=%d" % rc)
@@ -131,7 +135,7 @@ def field_op(field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
     out = np.zeros_like(a)
-    L = 6 if field in (2, 4) else 4
+    L = {2: 6, 4: 6, 8: 12, 9: 6}.get(field, 4)
     rc = lib().ref_field_op(field, op, _p(a), _p(b), _p(out), a.size // L)
     if rc != 0:
         raise RuntimeError("ref_field_op rc=%d" % rc)

@@ -43,7 +43,7 @@ static inline void FP(add)(FP(t)* z, const FP(t)* x, const FP(t)* y) {
     t[i] = (uint64_t)c;
     c >>= 64;
   }
-  if (FP(geq_q)(t)) FP(sub_q)(t); /* q has a spare top bit: no carry out */
+  if (c || FP(geq_q)(t)) FP(sub_q)(t); /* c is always 0 when q has a spare top bit; full-width moduli (secp256k1) carry out */
   for (int i = 0; i < NL; i++) z->l[i] = t[i];
 }
 static inline void FP(dbl)(FP(t)* z, const FP(t)* x) { FP(add)(z, x, x); }
@@ -75,6 +75,40 @@ static inline void FP(neg)(FP(t)* z, const FP(t)* x) {
  * of the reference's portable path (ecc/bn254/fp/element_purego.go:46-213; the spare top bit of q makes
  * the final word addition carry-free, field/generator/config/field_config.go:203-206); same result as the
  * textbook CIOS _mulGeneric fp/element.go:470-591. */
+#ifdef FP_FULL
+/* full-width modulus (no spare top bit: secp256k1 fp and fr): the reference generates the textbook CIOS with two extra words
+ * for these (_mulGeneric, ecc/secp256k1/fp/element.go; noCarry is false in field/generator/config/field_config.go:203-206) and
+ * the final subtraction looks at the carry word */
+static inline void FP(mul)(FP(t)* z, const FP(t)* x, const FP(t)* y) {
+  uint64_t t[NL + 2];
+  for (int j = 0; j < NL + 2; j++) t[j] = 0;
+  for (int i = 0; i < NL; i++) {
+    unsigned __int128 A;
+    uint64_t c = 0;
+    for (int j = 0; j < NL; j++) {
+      A = (unsigned __int128)x->l[j] * y->l[i] + t[j] + c;
+      t[j] = (uint64_t)A;
+      c = (uint64_t)(A >> 64);
+    }
+    A = (unsigned __int128)t[NL] + c;
+    t[NL] = (uint64_t)A;
+    t[NL + 1] = (uint64_t)(A >> 64);
+    const uint64_t m = t[0] * FP(QINV);
+    A = (unsigned __int128)m * FP(Q)[0] + t[0];
+    c = (uint64_t)(A >> 64);
+    for (int j = 1; j < NL; j++) {
+      A = (unsigned __int128)m * FP(Q)[j] + t[j] + c;
+      t[j - 1] = (uint64_t)A;
+      c = (uint64_t)(A >> 64);
+    }
+    A = (unsigned __int128)t[NL] + c;
+    t[NL - 1] = (uint64_t)A;
+    t[NL] = t[NL + 1] + (uint64_t)(A >> 64);
+  }
+  if (t[NL] || FP(geq_q)(t)) FP(sub_q)(t);
+  for (int i = 0; i < NL; i++) z->l[i] = t[i];
+}
+#else
 static inline void FP(mul)(FP(t)* z, const FP(t)* x, const FP(t)* y) {
   uint64_t t[NL];
   for (int j = 0; j < NL; j++) t[j] = 0;
@@ -98,6 +132,7 @@ static inline void FP(mul)(FP(t)* z, const FP(t)* x, const FP(t)* y) {
   if (FP(geq_q)(t)) FP(sub_q)(t);
   for (int i = 0; i < NL; i++) z->l[i] = t[i];
 }
+#endif
 static inline void FP(sqr)(FP(t)* z, const FP(t)* x) { FP(mul)(z, x, x); }
 static inline void FP(from_mont)(FP(t)* z, const FP(t)* x) {
   FP(t) one;

@@ -1,6 +1,7 @@
 /* group_tmpl.h -- curve group + MSM template of the CPU oracle (TEST INFRASTRUCTURE).
  *   #define K(name)  coordinate field prefix (Fp or Fp2 instance)
- *   #define FR(name) scalar field prefix (4 limbs)     #define FR_BITS 254|255
+ *   #define FR(name) scalar field prefix     #define FR_BITS 254|255|...     #define FR_NL its 64-bit limbs (4; 6 for bw6-761)
+ *   #define IMPL_C_OK(c) the window widths the reference implements for this curve (implementedCs, multiexp.go:77)
  *   #define GP(name) group prefix
  * Restates (reference tree, ecc/bn254; ecc/bls12-381 is the same generated code):
  *   g1.go:822-985 addMixed/subMixed/doubleMixed/doubleNegMixed, :736-817 add/double,
@@ -166,6 +167,7 @@ static int GP(best_c)(size_t n) { /* multiexp.go:75-93 */
   double mn = 1e300;
   int C = 4;
   for (int c = 4; c <= 16; c++) {
+    if (!(IMPL_C_OK(c))) continue;
     double cc = (double)(FR_BITS + 1) * (double)(n + ((size_t)1 << c));
     double cost = cc / (double)c;
     if (cost < mn) { mn = cost; C = c; }
@@ -187,7 +189,7 @@ static void GP(partition_range)(const FR(t)* scalars, size_t lo, size_t hi, size
     for (int ch = 0; ch < W; ch++) {
       uint64_t jc = (uint64_t)ch * c, idx = jc / 64, shift = jc - idx * 64;
       int64_t d = carry + (int64_t)((k.l[idx] & (mask << shift)) >> shift);
-      int multi = (64 % c != 0) && shift > (uint64_t)(64 - c) && idx < 3;
+      int multi = (64 % c != 0) && shift > (uint64_t)(64 - c) && idx < FR_NL - 1;
       if (multi) {
         uint64_t nb_hi = shift - (64 - c);
         d += (int64_t)((k.l[idx + 1] & (((uint64_t)1 << nb_hi) - 1)) << (c - nb_hi));
@@ -502,11 +504,11 @@ static int GP(msm)(const GP(aff)* points, const FR(t)* scalars, size_t n, int fo
   return 0;
 }
 
-/* [k]P, k a 4-limb canonical integer, double-and-add */
-static void GP(scalar_mul)(GP(aff)* out, const GP(aff)* p, const uint64_t k[4]) {
+/* [k]P, k an FR_NL-limb canonical integer, double-and-add */
+static void GP(scalar_mul)(GP(aff)* out, const GP(aff)* p, const uint64_t* k) {
   GP(xyzz) acc;
   GP(xyzz_set_inf)(&acc);
-  for (int i = 255; i >= 0; i--) {
+  for (int i = 64 * FR_NL - 1; i >= 0; i--) {
     GP(xyzz_double)(&acc, &acc);
     if ((k[i >> 6] >> (i & 63)) & 1) GP(add_mixed)(&acc, p, 0);
   }
@@ -545,7 +547,7 @@ static void* GP(gen_worker)(void* a_) {
   for (size_t l = 0; l < lanes; l++) {
     size_t idx = a->lo + l * len;
     if (idx >= a->hi) break;
-    uint64_t k[4] = {a->start + idx, 0, 0, 0};
+    uint64_t k[FR_NL] = {a->start + idx};
     GP(scalar_mul)(&cur[l], a->base, k);
     active++;
   }

@@ -160,6 +160,37 @@ FIELDS = {
         4,
         dict(qinvneg=725501752471715839, rsquare=[2726216793283724667, 14712177743343147295, 12091039717619697043, 81024008013859129]),
     ),
+    # N4 remainder: ecc/secp256k1/fp/element.go:31,71,801-806 ; fr/element.go:31,71,801-806 (moduli without a spare top bit)
+    "secp256k1_fp": Field(
+        "secp256k1_fp",
+        0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFFC2F,
+        4,
+        dict(qinvneg=15580212934572586289, rsquare=[8392367050913, 1, 0, 0]),
+    ),
+    "secp256k1_fr": Field(
+        "secp256k1_fr",
+        0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+        4,
+        dict(qinvneg=5408259542528602431, rsquare=[9902555850136342848, 8364476168144746616, 16616019711348246470, 11342065889886772165]),
+    ),
+    # ecc/bw6-761/fp/element.go:31,87,1546-1559 (12 words) ; fr/element.go:31,75,928-935 (6 words, = the bls12-377 base field)
+    "bw6761_fp": Field(
+        "bw6761_fp",
+        0x122E824FB83CE0AD187C94004FAFF3EB926186A81D14688528275EF8087BE41707BA638E584E91903CEBAFF25B423048689C8ED12F9FD9071DCD3DC73EBFF2E98A116C25667A8F8160CF8AEEAF0A437E6913E6870000082F49D00000000008B,
+        12,
+        dict(qinvneg=744663313386281181,
+             rsquare=[14305184132582319705, 8868935336694416555, 9196887162930508889, 15486798265448570248, 5402985275949444416,
+                      10893197322525159598, 3204916688966998390, 12417238192559061753, 12426306557607898622, 1305582522441154384,
+                      10311846026977660324, 48736111365249031]),
+    ),
+    "bw6761_fr": Field(
+        "bw6761_fr",
+        0x1AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001,
+        6,
+        dict(qinvneg=9586122913090633727,
+             rsquare=[13224372171368877346, 227991066186625457, 2496666625421784173, 13825906835078366124, 9475172226622360569,
+                      30958721782860680]),
+    ),
 }
 
 
@@ -576,10 +607,46 @@ def _mk_groups():
             ),
         ),
     )
+    # N4 remainder.  ecc/secp256k1/secp256k1.go:48-55 : Y^2 = X^3 + 7, the SEC2 generator
+    g["secp256k1_g1"] = Group(
+        "secp256k1_g1",
+        FpOps(FIELDS["secp256k1_fp"]),
+        FIELDS["secp256k1_fr"],
+        7,
+        (
+            55066263022277343669578718895168534326250603453777594175500187360389116729240,
+            32670510020758816978083085130507043184471273380659243275938904335757337482424,
+        ),
+    )
+    # ecc/bw6-761/bw6-761.go:92-103 : G1 Y^2 = X^3 - 1 and the M-twist G2 Y^2 = X^3 + 4, BOTH over Fp (12 words); fr 377 bits
+    K = FpOps(FIELDS["bw6761_fp"])
+    g["bw6761_g1"] = Group(
+        "bw6761_g1",
+        K,
+        FIELDS["bw6761_fr"],
+        K.neg(1),
+        (
+            6238772257594679368032145693622812838779005809760824733138787810501188623461307351759238099287535516224314149266511977132140828635950940021790489507611754366317801811090811367945064510304504157188661901055903167026722666149426237,
+            2101735126520897423911504562215834951148127555913367997162789335052900271653517958562461315794228241561913734371411178226936527683203879553093934185950470971848972085321797958124416462268292467002957525517188485984766314758624099,
+        ),
+    )
+    g["bw6761_g2"] = Group(
+        "bw6761_g2",
+        K,
+        FIELDS["bw6761_fr"],
+        4,
+        (
+            6445332910596979336035888152774071626898886139774101364933948236926875073754470830732273879639675437155036544153105017729592600560631678554299562762294743927912429096636156401171909259073181112518725201388196280039960074422214428,
+            562923658089539719386922163444547387757586534741080263946953401595155211934630598999300396317104182598044793758153214972605680357108252243146746187917218885078195819486220416605630144001533548163105316661692978285266378674355041,
+        ),
+    )
     return g
 
 
 GROUPS = _mk_groups()
+
+# implementedCs of each curve's MultiExp (multiexp.go:77): what bestC may return
+IMPLEMENTED_CS = {"secp256k1_g1": tuple(range(4, 16)), "bw6761_g1": (4, 5, 8, 10, 16), "bw6761_g2": (4, 5, 8, 10, 16)}
 
 
 # --------------------------------------------------------------------------------------

@@ -310,7 +310,7 @@ int emu_finalize(const void* partials, int nranks, int c, int tables, void* out_
 }  // namespace
 
 #ifndef EMU_GROUP
-#error "compile with -DEMU_GROUP=0..5"
+#error "compile with -DEMU_GROUP=0..8"
 #endif
 #if EMU_GROUP == 0
 using EmuG = bn254_g1;
@@ -322,8 +322,14 @@ using EmuG = bls12381_g1;
 using EmuG = bls12381_g2;
 #elif EMU_GROUP == 4
 using EmuG = bls12377_g1;
-#else
+#elif EMU_GROUP == 5
 using EmuG = bls12377_g2;
+#elif EMU_GROUP == 6
+using EmuG = secp256k1_g1;
+#elif EMU_GROUP == 7
+using EmuG = bw6761_g1;
+#else
+using EmuG = bw6761_g2;
 #endif
 #define EMU_CAT2(a, b) a##b
 #define EMU_CAT(a, b) EMU_CAT2(a, b)

@@ -1,4 +1,4 @@
-"""Generates tests/golden/msm_vectors.json: small MultiExp known answers for the six groups.
+"""Generates tests/golden/msm_vectors.json: small MultiExp known answers for every group of oracle.GROUPS.
 
 The reference holds no golden MSM output and cannot run here (Go), so these vectors are produced by the
 pinned Python oracle (oracle/oracle.py: restatement of ecc/<curve>/multiexp.go, pinned to the reference's constants and

@@ -81,7 +81,7 @@ def check_fr_from_mont(G, run):
     rng = random.Random(5)
     vals = [0, 1, fr.q - 1, fr.Rmod] + [rng.randrange(fr.q) for _ in range(30)]
     A = u32(np.array([fr.to_limbs(v) for v in vals], dtype=np.uint64))
-    out = run(OPS["FR_FROM_MONT"], A, None, 8)
+    out = run(OPS["FR_FROM_MONT"], A, None, 2 * fr.limbs)
     got = [O.Field.from_limbs([int(x) for x in r]) for r in np.ascontiguousarray(out).view(np.uint64)]
     assert got == [fr.from_mont(v) for v in vals]
 

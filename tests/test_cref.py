@@ -7,7 +7,8 @@ import pytest
 from oracle import cref
 from oracle import oracle as O
 
-FIELD_IDS = {"bn254_fp": 0, "bn254_fr": 1, "bls12381_fp": 2, "bls12381_fr": 3, "bls12377_fp": 4, "bls12377_fr": 5}
+FIELD_IDS = {"bn254_fp": 0, "bn254_fr": 1, "bls12381_fp": 2, "bls12381_fr": 3, "bls12377_fp": 4, "bls12377_fr": 5,
+             "secp256k1_fp": 6, "secp256k1_fr": 7, "bw6761_fp": 8, "bw6761_fr": 9}
 
 
 def _limbs(f, vals):
@@ -174,7 +175,7 @@ def test_golden_msm_vectors(g):
 
     pts, s, want = load_golden_msm(g)
     G = O.GROUPS[g]
-    assert pts.shape == (96, G.aff_words) and s.shape == (96, 4)
+    assert pts.shape == (96, G.aff_words) and s.shape == (96, G.fr.limbs)
     for c in (0, 4, 9, 12, 16):
         got, _, _, _ = cref.msm(g, pts, s, c=c, nthreads=2)
         assert np.array_equal(got, want), c

@@ -36,7 +36,7 @@ def _lib():
             os.path.join(EMU, f) for f in os.listdir(EMU)]
         if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in deps):
             objs, procs = [], []
-            for k in range(6):
+            for k in range(len(GROUPS)):
                 o = os.path.join(bdir, "emu_%d.o" % k)
                 objs.append(o)
                 # tests/emu FIRST: its cuda_runtime.h stands in for the real one
@@ -130,7 +130,8 @@ def test_emulated_kernels_skewed_inputs(kind, tables):
         _check(g, emu_msm(g, pts, s, c, tables=tables, K=K, K2_first=4, K2=4, split=split), want)
 
 
-@pytest.mark.parametrize("g,n", [("bn254_g2", 300), ("bls12381_g1", 400), ("bls12381_g2", 150), ("bls12377_g1", 300), ("bls12377_g2", 120)])
+@pytest.mark.parametrize("g,n", [("bn254_g2", 300), ("bls12381_g1", 400), ("bls12381_g2", 150), ("bls12377_g1", 300), ("bls12377_g2", 120),
+                                 ("secp256k1_g1", 400), ("bw6761_g1", 150), ("bw6761_g2", 120)])
 def test_emulated_kernels_other_groups(g, n):
     pts, s = make_inputs(g, n, 99)
     want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)

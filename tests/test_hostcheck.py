@@ -19,7 +19,7 @@ _LIBS = {}
 
 
 def _build(variant):
-    """six per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
+    """per-group objects + the dispatcher, compiled in parallel; rebuilt only when a header is newer than the .so"""
     if variant not in _LIBS:
         tag = {"portable": "", "emulated": "_emu", "emulated_sqr": "_emusqr", "emulated_fp2dot": "_emufp2dot", "emulated_fp2lazy": "_emufp2lazy", "portable_fp2lazy": "_fp2lazy", "emulated_kara": "_emukara", "portable_kara": "_kara", "emulated_dot4": "_emudot4"}[variant]
         out = OUT % tag
@@ -36,7 +36,7 @@ def _build(variant):
                                                      "emulated_dot4": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1", "-DGMSM_DOT4=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
-            for k in list(range(6)) + [None]:
+            for k in list(range(len(O.GROUPS))) + [None]:
                 o = os.path.join(bdir, "hostcheck%s_%s.o" % (tag, "d" if k is None else k))
                 objs.append(o)
                 procs.append(subprocess.Popen(["g++", *flags, *([] if k is None else ["-DHC_GROUP=%d" % k]), "-c", "-o", o, src]))
@@ -65,7 +65,8 @@ def hc(request):
 
 def _runner(hc, g):
     cid = list(O.GROUPS).index(g)
-    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1", "bls12377_g2"]
+    assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1", "bls12377_g2", "secp256k1_g1",
+                              "bw6761_g1", "bw6761_g2"]
 
     def run(op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)
@@ -92,7 +93,7 @@ def test_point_ops_host(hc, g):
 
 
 @pytest.mark.parametrize("g,c", [("bn254_g1", 5), ("bn254_g1", 22), ("bn254_g2", 7), ("bls12381_g1", 11), ("bls12381_g2", 3),
-                                 ("bls12377_g1", 9), ("bls12377_g2", 4)])
+                                 ("bls12377_g1", 9), ("bls12377_g2", 4), ("secp256k1_g1", 8), ("bw6761_g1", 6), ("bw6761_g2", 5)])
 def test_table_level_host(hc, g, c):
     """one level of the window tables (k_table_level's batch function, built for the CPU): out_i = 2^c * in_i in affine
     normal form, infinity preserved, ragged batch (19 = 2 full batches of 8 + 3)"""
@@ -118,7 +119,7 @@ def test_table_level_host(hc, g, c):
 
 def test_window_plan(hc):
     buf = (ctypes.c_int * 6)()
-    for bits in (253, 254, 255):
+    for bits in (253, 254, 255, 256, 377):
         for c in range(2, 25):
             hc.hostcheck_plan(bits, c, buf)
             W = O.compute_nb_chunks(bits, c)
@@ -126,7 +127,7 @@ def test_window_plan(hc):
             assert list(buf) == [c, W, lc, 1 << (c - 1), 1 << (lc - 1), (W - 1) * (1 << (c - 1)) + (1 << (lc - 1))]
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1", "secp256k1_g1", "bw6761_g1"])
 def test_carry_chain_mul_sqr_stress(g):
     """the device formulation of Mul / Square (emulated) against the portable path and big-int arithmetic on many random
     and extreme operands (limbs of all-ones, single bits, q-1, values next to the limb boundaries)"""
@@ -169,6 +170,12 @@ def test_carry_chain_mul_sqr_stress(g):
     lim = lambda M: [f.from_limbs(row) for row in np.ascontiguousarray(M).view(np.uint64)]
     a_, b_, c_, d_ = lim(A), lim(B), lim(C), lim(D)
     assert lim(outs[1]) == [(x * y + u * v) * f.Rinv % f.q for x, y, u, v in zip(a_, b_, c_, d_)]
+    # additions / doublings / subtractions of the same extreme operands (full-width moduli: the carry out of the limbs decides
+    # the final subtraction, field.cuh fp_reduce_once)
+    for op, fn in ((1, lambda x, y: (x + y) % f.q), (2, lambda x, y: (x - y) % f.q)):
+        for run in (run_p, run_e):
+            assert lim(run(op, A, B, nl)) == [fn(x, y) for x, y in zip(a_, b_)]
+    assert lim(run_e(5, A, None, nl)) == [2 * x % f.q for x in a_]
     got_m = [f.from_limbs(row) for row in me.view(np.uint64)]
     got_s = [f.from_limbs(row) for row in se.view(np.uint64)]
     assert got_m == [vals[i] * vals[perm[i]] * f.Rinv % f.q for i in range(len(vals))]
