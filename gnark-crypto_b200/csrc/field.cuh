@@ -242,8 +242,8 @@ GMSM_HD Fp<P> fp_neg(const Fp<P>& a) {
 // Montgomery multiplication  z = x*y*R^-1 mod q   (F1)
 // ------------------------------------------------------------------------------------------
 // Textbook CIOS on 32-bit limbs with the two extra words (_mulGeneric, fp/element.go:470-591, at half the word size): the host
-// build's multiplier and, on the device, the multiplier of the FULL-width moduli -- the even/odd-accumulator form below drops
-// carries that only the spare top bit makes zero (T < 2q < 2^(32N)); here the carry limb t[N] joins the final subtraction.
+// build's multiplier (the carry limb t[N] joins the final subtraction: zero for the moduli with a spare top bit, live for the
+// FULL-width ones) and the reference the device formulation below is tested against.
 template <class P>
 GMSM_HD Fp<P> fp_mul_cios(const Fp<P>& x, const Fp<P>& y) {
   constexpr int N = P::N;
@@ -285,10 +285,13 @@ GMSM_HD Fp<P> fp_mul_cios(const Fp<P>& x, const Fp<P>& y) {
 template <class P>
 GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   constexpr int N = P::N;
-  if constexpr (P::FULL) return fp_mul_cios(x, y);
   Fp<P> r;
 #if defined(GMSM_PTX_PATH) && !defined(GMSM_PORTABLE_MUL)
   // Two accumulators, N+2 slots each: [0..N-1] limbs, [N] carry limb, [N+1] always zero.
+  // Full-width moduli (P::FULL, secp256k1): T < 2q no longer fits N limbs, so the two carries that the spare top bit makes
+  // zero are kept -- the carry out of the odd accumulator's reduction chain (step 5) goes to ITS carry limb, which the next
+  // row (where that accumulator is the even one) adds to instead of overwriting, and the last row's joins the final sum as
+  // limb N, the carry fp_reduce_once takes.  Two more ADDCs per row; everything else is unchanged.
   uint32_t A[N + 2], B[N + 2];
 #pragma unroll
   for (int i = 0; i < N + 2; i++) A[i] = B[i] = 0;
@@ -316,7 +319,8 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
       Ev[j] = madc_lo_cc(x.l[j], bi, Ev[j]);
       Ev[j + 1] = madc_hi_cc(x.l[j], bi, Ev[j + 1]);
     }
-    Ev[N] = addc(0, 0);
+    if constexpr (P::FULL) Ev[N] = addc(Ev[N], 0);   // (Ev was the previous row's Od: its carry limb is live)
+    else Ev[N] = addc(0, 0);
     // step 2: Od = (Od >> 2 limbs) + x_odd * bi   (no carry out; Od[N+1] == 0)
     Od[0] = mad_lo_cc(x.l[1], bi, Od[2]);
     Od[1] = madc_hi_cc(x.l[1], bi, Od[3]);
@@ -345,6 +349,7 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
       Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
       Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
     }
+    if constexpr (P::FULL) Od[N] = addc(0, 0);
     e0prev = Ev[0];
     dprev = d;
   }
@@ -354,8 +359,13 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
   r.l[0] = addc_cc(A[0], B[1]);
 #pragma unroll
   for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(A[i], B[i + 1]);
-  r.l[N - 1] = addc(A[N - 1], B[N]);
-  fp_reduce_once(r);
+  if constexpr (P::FULL) {
+    r.l[N - 1] = addc_cc(A[N - 1], B[N]);
+    fp_reduce_once(r, addc(A[N], 0));
+  } else {
+    r.l[N - 1] = addc(A[N - 1], B[N]);
+    fp_reduce_once(r);
+  }
 #else
   return fp_mul_cios(x, y);
 #endif

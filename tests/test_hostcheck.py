@@ -36,7 +36,7 @@ def _build(variant):
                                                      "emulated_dot4": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1", "-DGMSM_DOT4=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
-            for k in list(range(len(O.GROUPS))) + [None]:
+            for k in list(range(len(O.GROUPS) + 1)) + [None]:     # + the field-only pseudo group 9 (secp256k1 fr)
                 o = os.path.join(bdir, "hostcheck%s_%s.o" % (tag, "d" if k is None else k))
                 objs.append(o)
                 procs.append(subprocess.Popen(["g++", *flags, *([] if k is None else ["-DHC_GROUP=%d" % k]), "-c", "-o", o, src]))
@@ -64,7 +64,7 @@ def hc(request):
 
 
 def _runner(hc, g):
-    cid = list(O.GROUPS).index(g)
+    cid = 9 if g == "secp256k1_fr" else list(O.GROUPS).index(g)
     assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1", "bls12377_g2", "secp256k1_g1",
                               "bw6761_g1", "bw6761_g2"]
 
@@ -127,12 +127,12 @@ def test_window_plan(hc):
             assert list(buf) == [c, W, lc, 1 << (c - 1), 1 << (lc - 1), (W - 1) * (1 << (c - 1)) + (1 << (lc - 1))]
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1", "secp256k1_g1", "bw6761_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1", "secp256k1_g1", "secp256k1_fr", "bw6761_g1"])
 def test_carry_chain_mul_sqr_stress(g):
     """the device formulation of Mul / Square (emulated) against the portable path and big-int arithmetic on many random
-    and extreme operands (limbs of all-ones, single bits, q-1, values next to the limb boundaries)"""
-    G = O.GROUPS[g]
-    f = G.K.f
+    and extreme operands (limbs of all-ones, single bits, q-1, values next to the limb boundaries).  secp256k1's two moduli
+    fill all 256 bits: the multiplier keeps the carries a spare top bit would make zero (field.cuh, P::FULL)"""
+    f = O.FIELDS[g] if g.endswith("_fr") else O.GROUPS[g].K.f
     rng = np.random.default_rng(17)
     nl = f.limbs * 2
     import random
@@ -158,7 +158,7 @@ def test_carry_chain_mul_sqr_stress(g):
     # the experimental fused two-product routine: (x*y + u*v) R^-1 with one reduction, against big-int arithmetic and
     # against its plain composition (two products and an addition) in the portable build
     C, D = A[rng.permutation(len(vals))], A[rng.permutation(len(vals))]
-    cid = list(O.GROUPS).index(g)
+    cid = 9 if g == "secp256k1_fr" else list(O.GROUPS).index(g)
     outs = []
     for variant in ("portable", "emulated_sqr"):
         out = np.zeros_like(A)
