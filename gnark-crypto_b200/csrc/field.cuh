@@ -1050,26 +1050,26 @@ GMSM_HD Fp<P> fp_inv_fermat(const Fp<P>& x) {
 // Montgomery products of the Fermat ladder: the inversion at the end of an MSM (FromJacobian, g1.go:150-166) sits on the
 // serial tail, where one product costs ~0.5 us of latency.  (The reference uses Pornin's optimised binary GCD,
 // fp/element.go:1173-1325; any correct inverse is limb-identical.)  a^-1 = x^-1 R^-1, so two products by R^2 bring the
-// result back to Montgomery form.  Inverse(0) = 0.  Needs one spare top bit in q (x1 + q must fit the limbs).
+// result back to Montgomery form.  Inverse(0) = 0.  For a full-width q the bit of x1 + q above the limbs is shifted back in.
 template <class P>
 GMSM_HD Fp<P> fp_inv(const Fp<P>& x) {
   constexpr int N = P::N;
-  if constexpr (P::FULL) return fp_inv_fermat(x);   // x1 + q does not fit the limbs without a spare top bit
   if (x.is_zero()) return x;
   uint32_t u[N], v[N], x1[N], x2[N];
   for (int i = 0; i < N; i++) { u[i] = x.l[i]; v[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
   x1[0] = 1;
   auto is_one = [](const uint32_t* a) { uint32_t o = a[0] ^ 1u; for (int i = 1; i < N; i++) o |= a[i]; return o == 0; };
-  auto shr1 = [](uint32_t* a) { for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[N - 1] >>= 1; };
-  auto add_mod = [](uint32_t* a) { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)a[i] + P::mod(i); a[i] = (uint32_t)c; c >>= 32; } };
+  // a = (top : a) >> 1 -- top is the bit above the limbs (the carry of y + q for a full-width q, otherwise 0)
+  auto shr1 = [](uint32_t* a, uint32_t top) { for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[N - 1] = (a[N - 1] >> 1) | (top << 31); };
+  auto add_mod = [](uint32_t* a) { uint64_t c = 0; for (int i = 0; i < N; i++) { c += (uint64_t)a[i] + P::mod(i); a[i] = (uint32_t)c; c >>= 32; } return (uint32_t)c; };
   auto geq = [](const uint32_t* a, const uint32_t* b) { for (int i = N - 1; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; } return true; };
   auto sub = [](uint32_t* a, const uint32_t* b) { uint64_t br = 0; for (int i = 0; i < N; i++) { uint64_t d = (uint64_t)a[i] - b[i] - br; a[i] = (uint32_t)d; br = (d >> 32) & 1; } return (uint32_t)br; };
   auto halve = [&](uint32_t* w, uint32_t* y) {   // w even: w /= 2, y /= 2 mod q
-    shr1(w);
-    if (y[0] & 1u) add_mod(y);
-    shr1(y);
+    shr1(w, 0);
+    const uint32_t top = (y[0] & 1u) ? add_mod(y) : 0u;   // y + q < 2q: one bit above the limbs when q fills them (P::FULL)
+    shr1(y, top);
   };
-  auto sub_mod = [&](uint32_t* a, const uint32_t* b) { if (sub(a, b)) add_mod(a); };   // a = a - b mod q (a, b < q)
+  auto sub_mod = [&](uint32_t* a, const uint32_t* b) { if (sub(a, b)) add_mod(a); };   // a = a - b mod q (a, b < q; the wrap is exact)
   while (!is_one(u) && !is_one(v)) {
     while (!(u[0] & 1u)) halve(u, x1);
     while (!(v[0] & 1u)) halve(v, x2);

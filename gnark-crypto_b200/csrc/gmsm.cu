@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <condition_variable>
 #include <cstdarg>
@@ -104,9 +105,9 @@ static const WidthModel& width_model(int curve) {
   static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
   static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
   static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}};
-  // N4 remainder: fitted from one width sweep each (profiles/r02_n4_new_curves.txt)
-  static const WidthModel secp256k1_g1 = {0.30, {4.6, 4.4, 3.9, 4.0, 4.3, 6.7, 11.3}};
-  static const WidthModel bw6761 = {1.50, {21.0, 21.0, 17.7, 18.4, 23.0, 27.5, 34.0}};
+  // N4 remainder: fitted from one width sweep each (profiles/r02_n4_new_curves_call11.txt)
+  static const WidthModel secp256k1_g1 = {0.1755, {2.76, 2.78, 3.20, 3.27, 3.70, 4.42, 6.50}};
+  static const WidthModel bw6761 = {1.63, {18.5, 18.2, 19.9, 20.6, 27.2, 31.5, 51.0}};
   switch (curve) {
     case GMSM_SECP256K1_G1: return secp256k1_g1;
     case GMSM_BW6761_G1: case GMSM_BW6761_G2: return bw6761;
@@ -123,8 +124,10 @@ static double model_ms(int curve, int fr_bits, size_t n, int c) {
   if (c < 13) tail = m.tail_ms[0] * (1.0 + 0.03 * (13 - c));        // more windows: longer Horner / more launches, fewer buckets
   else if (c > 19) tail = m.tail_ms[6] * (double)(1u << (c - 19));  // bucket reduction doubles per bit
   else tail = m.tail_ms[c - 13];
-  // a last window of 1-2 bits (e.g. c = 23 for 254-bit scalars) puts all its entries on 1-2 buckets: never worth it
-  if (p.last_c <= 2 && p.nwin > 1) tail += 1e-6 * (double)n * 0.5;
+  // a narrow last window puts all its n entries on a handful of buckets: the histogram / rank atomics of K1 serialise on those
+  // addresses.  Measured on secp256k1 (fr.Bits = 256 = 16 * 16) at 2^24: +5.6 ms with 2 buckets (c = 15, 17), +2.7 ms with 16
+  // (c = 18), nothing at c = 16 (profiles/r02_n4_new_curves_call11.txt): ~0.4 / cbrt(buckets) ns per entry up to 256 buckets
+  if (p.nwin > 1 && p.nb_last <= 256) tail += 1e-6 * (double)n * 0.4 / std::cbrt((double)p.nb_last);
   const double e_ns = m.add_ns * (1.0 + 0.012 * std::max(0, c - 17)) + 0.009;
   return (double)n * p.nwin * e_ns * 1e-6 + tail;
 }

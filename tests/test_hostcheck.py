@@ -176,6 +176,10 @@ def test_carry_chain_mul_sqr_stress(g):
         for run in (run_p, run_e):
             assert lim(run(op, A, B, nl)) == [fn(x, y) for x, y in zip(a_, b_)]
     assert lim(run_e(5, A, None, nl)) == [2 * x % f.q for x in a_]
+    # inversion (binary GCD; for the full-width moduli the bit of y + q above the limbs is shifted back in): inv(xR) = x^-1 R
+    sel = list(range(0, len(vals), 17))
+    inv = lim(run_e(6, A[sel], None, nl))
+    assert inv == [(pow(a_[i], -1, f.q) * f.R2 % f.q) if a_[i] else 0 for i in sel]
     got_m = [f.from_limbs(row) for row in me.view(np.uint64)]
     got_s = [f.from_limbs(row) for row in se.view(np.uint64)]
     assert got_m == [vals[i] * vals[perm[i]] * f.Rinv % f.q for i in range(len(vals))]
