@@ -99,15 +99,19 @@ static const GroupVTable* vtable(int curve) {
 struct WidthModel {
   double add_ns;          // accumulate: ns per mixed addition at c <= 17
   double tail_ms[7];      // tail_g(c) for c = 13 .. 19
+  double fixed_ms;        // beyond c = 19: tail = fixed_ms + red19_ms * 2^(c - 19) (the bucket reduction doubles per bit, the carry
+  double red19_ms;        //   join / Horner / inversion do not); red19_ms = 0: the older rule tail_ms[6] * 2^(c - 19)
 };
 static const WidthModel& width_model(int curve) {
-  static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}};
-  static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}};
-  static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}};
-  static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}};
-  // N4 remainder: fitted from one width sweep each (profiles/r02_n4_new_curves_call11.txt)
-  static const WidthModel secp256k1_g1 = {0.1755, {2.76, 2.78, 3.20, 3.27, 3.70, 4.42, 6.50}};
-  static const WidthModel bw6761 = {1.63, {18.5, 18.2, 19.9, 20.6, 27.2, 31.5, 51.0}};
+  static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}, 0, 0};
+  static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}, 0, 0};
+  static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}, 0, 0};
+  static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}, 0, 0};
+  // N4 remainder: fitted from the width sweeps of profiles/r02_n4_new_curves_call11.txt / _call12.txt.  secp256k1: fr.Bits = 256
+  // makes the last window narrow for most widths (K1 contention, below); its c = 19 entry carries the measured 2 ms of that
+  // (512 buckets).  bw6-761: the 377 doublings of the 24-limb Horner chain alone are ~9 ms.
+  static const WidthModel secp256k1_g1 = {0.1755, {2.50, 2.50, 2.95, 3.08, 3.45, 4.17, 7.66}, 2.05, 3.30};
+  static const WidthModel bw6761 = {1.63, {16.8, 16.5, 17.7, 19.3, 25.9, 30.2, 46.6}, 13.2, 33.4};
   switch (curve) {
     case GMSM_SECP256K1_G1: return secp256k1_g1;
     case GMSM_BW6761_G1: case GMSM_BW6761_G2: return bw6761;
@@ -122,7 +126,8 @@ static double model_ms(int curve, int fr_bits, size_t n, int c) {
   const WindowPlan p = make_plan(fr_bits, c);
   double tail;
   if (c < 13) tail = m.tail_ms[0] * (1.0 + 0.03 * (13 - c));        // more windows: longer Horner / more launches, fewer buckets
-  else if (c > 19) tail = m.tail_ms[6] * (double)(1u << (c - 19));  // bucket reduction doubles per bit
+  else if (c > 19) tail = m.red19_ms > 0 ? m.fixed_ms + m.red19_ms * (double)(1u << (c - 19))
+                                         : m.tail_ms[6] * (double)(1u << (c - 19));  // bucket reduction doubles per bit
   else tail = m.tail_ms[c - 13];
   // a narrow last window puts all its n entries on a handful of buckets: the histogram / rank atomics of K1 serialise on those
   // addresses.  Measured on secp256k1 (fr.Bits = 256 = 16 * 16) at 2^24: +5.6 ms with 2 buckets (c = 15, 17), +2.7 ms with 16
@@ -302,7 +307,12 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   if (const char* e = getenv("GMSM_AFFINE")) ctx->affine = atoi(e) != 0;
   if (shared) ctx->affine = false;   // the window-table mode has one accumulation path
   if (const char* e = getenv("GMSM_TABLE_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 256) ctx->table_passes = v; }
-  if (const char* e = getenv("GMSM_QUAD")) ctx->quad_mode = atoi(e);
+  // lane-parallel tail kernels (csrc/quad.cuh), default off: measured slower for the 8- and 12-limb groups.
+  // bw6-761 (24 limbs: one field product is ~9x bn254's, the serial Horner chain ~10 ms) takes them for the Horner / inversion
+  // kernel and for small bucket reductions: 2^18 28.6 -> 27.3 ms, 2^14 17.3 -> 14.8 ms; large reductions stay one thread per
+  // segment (2^22: 176.6 vs 186.0 ms with quads everywhere) -- profiles/r02_n4_new_curves_call12.txt
+  if (curve == GMSM_BW6761_G1 || curve == GMSM_BW6761_G2) { ctx->quad_mode = 1; ctx->quad_max_items = 20000; }
+  if (const char* e = getenv("GMSM_QUAD")) { ctx->quad_mode = atoi(e); ctx->quad_max_items = (size_t)1 << 40; }
   if (const char* e = getenv("GMSM_QUAD_MAX")) { long v = atol(e); if (v >= 0) ctx->quad_max_items = (size_t)v; }
   if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = ctx->split_tab = v; }
   ctx->plan = make_plan(ci.fr_bits, c);

@@ -102,8 +102,13 @@ def test_window_model_choices_are_pinned():
     BN_G1, BN_G2, BLS_G1, BLS_G2, B377_G1 = 0, 1, 2, 3, 4
     want = {(BN_G1, 16): 15, (BN_G1, 18): 15, (BN_G1, 20): 17, (BN_G1, 22): 17, (BN_G1, 23): 17, (BN_G1, 24): 17, (BN_G1, 26): 20,
             (BLS_G1, 20): 16, (BLS_G1, 22): 17, (BLS_G1, 24): 19, (BN_G2, 20): 17, (BN_G2, 22): 17, (BLS_G2, 20): 17, (B377_G1, 22): 17}
+    # N4 curves (profiles/r02_n4_new_curves_call11.txt, _call12.txt): secp256k1's 256-bit scalars make 16 | 256 and 20 (13 windows,
+    # a full-width last one) the good widths -- 15, 17, 18, 19 leave a last window of 1..9 bits whose few buckets serialise K1
+    SECP, BW6_G1, BW6_G2 = 6, 7, 8
+    want.update({(SECP, 16): 14, (SECP, 20): 16, (SECP, 22): 16, (SECP, 24): 20, (BW6_G1, 18): 14, (BW6_G1, 20): 16, (BW6_G1, 22): 18,
+                 (BW6_G1, 24): 19, (BW6_G2, 20): 16})
     for (curve, logn), c in want.items():
         assert L.gmsm_choose_window_bits(curve, 1 << logn) == c, (curve, logn)
-    for curve in (BN_G1, BN_G2, BLS_G1, BLS_G2):
+    for curve in (BN_G1, BN_G2, BLS_G1, BLS_G2, BW6_G1):
         cs = [L.gmsm_choose_window_bits(curve, 1 << k) for k in range(4, 28)]
         assert all(2 <= c <= 24 for c in cs) and all(b >= a for a, b in zip(cs, cs[1:])), cs     # wider windows for larger n
