@@ -37,9 +37,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CURVE_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255, "bls12377_g1": 253, "bls12377_g2": 253,
-              "secp256k1_g1": 256, "bw6761_g1": 377, "bw6761_g2": 377}
+              "secp256k1_g1": 256, "bw6761_g1": 377, "bw6761_g2": 377, "bls24315_g1": 253, "bls24317_g1": 255, "bw6633_g1": 315,
+              "bw6633_g2": 315}
 AFF_BYTES = {"bn254_g1": 64, "bn254_g2": 128, "bls12381_g1": 96, "bls12381_g2": 192, "bls12377_g1": 96, "bls12377_g2": 192,
-             "secp256k1_g1": 64, "bw6761_g1": 192, "bw6761_g2": 192}
+             "secp256k1_g1": 64, "bw6761_g1": 192, "bw6761_g2": 192, "bls24315_g1": 80, "bls24317_g1": 80, "bw6633_g1": 160,
+             "bw6633_g2": 160}
 FP2_GROUPS = ("bn254_g2", "bls12381_g2", "bls12377_g2")       # coordinates in Fp2 (G2 of bw6-761 is over Fp)
 FR_MOD = {
     256: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
@@ -48,6 +50,21 @@ FR_MOD = {
     255: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
     253: 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001,
 }
+# scalar-field moduli that share a bit length with one of the above (bls24-315: 253 bits like bls12-377, bls24-317: 255 like
+# bls12-381) are looked up by group first
+FR_Q = {
+    "bls24315_g1": 0x196DEAC24A9DA12B25FC7EC9CF927A98C8C480ECE644E36419D0C5FD00C00001,
+    "bls24317_g1": 0x443F917EA68DAFC2D0B097F28D83CD491CD1E79196BF0E7AF000000000000001,
+    "bw6633_g1": 0x4C23A02B586D650D3F7498BE97C5EAFDEC1D01AA27A1AE0421EE5DA52BDE5026FE802FF40300001,
+    "bw6633_g2": 0x4C23A02B586D650D3F7498BE97C5EAFDEC1D01AA27A1AE0421EE5DA52BDE5026FE802FF40300001,
+}
+
+
+def fr_mod(g):
+    """the scalar-field modulus of a group"""
+    return FR_Q.get(g) or fr_mod(g)
+
+
 BASE_MULT = 0xC0FFEE            # the synthetic bases are [start + i] * B with B = [BASE_MULT] * generator
 STAGE_NAMES = ["digits_hist", "scan", "scatter", "accumulate", "carries", "bucket_reduce", "finalize", "total"]
 
@@ -64,11 +81,11 @@ def scalar_words(bits):
     return (bits + 63) // 64
 
 
-def synth_scalars(n, bits, seed):
+def synth_scalars(n, bits, seed, q=None):
     """n uniform values < r as fr.Limbs x u64 limbs (mask top limb to fr.Bits, rejection-sample), read as
     the Montgomery representation -- the analogue of fr.SetRandom (fr/element.go:302-343)."""
     rng = np.random.default_rng(seed)
-    q = FR_MOD[bits]
+    q = q or FR_MOD[bits]
     nw = scalar_words(bits)
     ql = [np.uint64((q >> (64 * i)) & (2**64 - 1)) for i in range(nw)]
     out = np.empty((n, nw), dtype=np.uint64)
@@ -245,7 +262,7 @@ def run_reference(args, rank, world):
     # probe: one 2^20 step decides the per-step size (full size unless K + W steps of it would exceed the budget)
     probe_log = min(20, logn_total)
     pts = cref.generate_multiples(g, base, 1, 1 << probe_log, nthreads=cores)
-    s = synth_scalars(1 << probe_log, CURVE_BITS[g], 0x5EED0000 + 2)
+    s = synth_scalars(1 << probe_log, CURVE_BITS[g], 0x5EED0000 + 2, fr_mod(g))
     cref.msm(g, pts, s, c=0, nthreads=cores)
     t0 = time.perf_counter()
     cref.msm(g, pts, s, c=0, nthreads=cores)
@@ -257,7 +274,7 @@ def run_reference(args, rank, world):
     n = 1 << logs
     if n != (1 << probe_log):
         pts = cref.generate_multiples(g, base, 1, n, nthreads=cores)
-        s = synth_scalars(n, CURVE_BITS[g], 0x5EED0000 + 2)
+        s = synth_scalars(n, CURVE_BITS[g], 0x5EED0000 + 2, fr_mod(g))
     for _ in range(args.warmup):
         cref.msm(g, pts, s, c=0, nthreads=cores)
     times, used_c, leaves = [], 0, 0
@@ -302,7 +319,7 @@ def closed_form_check(X, g, result_jac, local_dot):
     local_dot: this rank's sum_i (start+i) * mont_limbs_i mod r; all ranks' sums are combined on rank 0."""
     import torch
 
-    r = FR_MOD[CURVE_BITS[g]]
+    r = fr_mod(g)
     dots = [local_dot]
     if X.world > 1:
         t = torch.tensor([(local_dot >> (32 * k)) & 0xFFFFFFFF for k in range(12)], dtype=torch.int64, device="cuda")
@@ -343,7 +360,7 @@ def measure_resident(X, g, logn_local, steps, warmup, c=0, kind=None, sample_clo
     d_B = eng.generate_multiples(_generator_limbs(g), BASE_MULT, 1)
     base = d_B.cpu().numpy().view(np.uint64).copy()
     d_points = eng.generate_multiples(base, 1 + lo, n)
-    h_scalars_np = synth_scalars(n, bits, 0x5EED0000 + 2 + rank)
+    h_scalars_np = synth_scalars(n, bits, 0x5EED0000 + 2 + rank, fr_mod(g))
     if kind:
         h_scalars_np = skew_scalars(h_scalars_np, kind)
     d_scalars = eng.to_device(h_scalars_np)
@@ -385,7 +402,7 @@ def measure_resident(X, g, logn_local, steps, warmup, c=0, kind=None, sample_clo
     result_jac = out.cpu().numpy().view(np.uint64).copy()
     # parity of the TIMED result at full size
     t0 = time.perf_counter()
-    ok = closed_form_check(X, g, result_jac, dot_index_mod(h_scalars_np, 1 + lo, FR_MOD[bits]))
+    ok = closed_form_check(X, g, result_jac, dot_index_mod(h_scalars_np, 1 + lo, fr_mod(g)))
     parity_s = time.perf_counter() - t0
     # stage times of the dominant kernel, averaged over a few more steps (events on the launch stream)
     acc_ms, stages = [], None
@@ -725,7 +742,7 @@ def two_in_flight(X, g, logn, steps):
     engs = [X.pkg.Engine(g, n, c=0, device=X.local_rank) for _ in range(2)]
     base = engs[0].generate_multiples(_generator_limbs(g), BASE_MULT, 1).cpu().numpy().view(np.uint64).copy()
     d_points = engs[0].generate_multiples(base, 1, n)
-    h_s = synth_scalars(n, CURVE_BITS[g], 0x5EED0000 + 2)
+    h_s = synth_scalars(n, CURVE_BITS[g], 0x5EED0000 + 2, fr_mod(g))
     d_s = engs[0].to_device(h_s)
     outs = [torch.zeros_like(engs[0]._out) for _ in range(2)]
     streams = [torch.cuda.Stream(device=X.local_rank) for _ in range(2)]
@@ -754,7 +771,7 @@ def two_in_flight(X, g, logn, steps):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / reps
     a, b = outs[0].cpu().numpy().view(np.uint64), outs[1].cpu().numpy().view(np.uint64)
-    ok = closed_form_check(X, g, a, dot_index_mod(h_s, 1, FR_MOD[CURVE_BITS[g]]))
+    ok = closed_form_check(X, g, a, dot_index_mod(h_s, 1, fr_mod(g)))
     for e in engs:
         e.close()
     return {"workload": "%s MultiExp n=2^%d, two calls in flight on two contexts / streams" % (g, logn), "ms_per_msm": ms,
@@ -771,7 +788,7 @@ def concurrent3(X, native, mx, g, logn):
     jobs = []
     for k in range(3):
         pts = eng.generate_multiples(base, 1 + k * n, n).cpu().numpy().view(np.uint64).copy()
-        sc = synth_scalars(n, CURVE_BITS[g], 0x5EED0100 + k)
+        sc = synth_scalars(n, CURVE_BITS[g], 0x5EED0100 + k, fr_mod(g))
         jobs.append((pts, sc, np.zeros(3 * wds // 2, dtype=np.uint64)))
     eng.close()
 

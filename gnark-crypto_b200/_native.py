@@ -19,6 +19,7 @@ SYMBOLS = [
     "gmsm_last_error", "gmsm_version", "gmsm_affine_bytes", "gmsm_scalar_bytes", "gmsm_jac_bytes", "gmsm_xyzz_bytes",
     "gmsm_bn254_g1_multiexp", "gmsm_bn254_g2_multiexp", "gmsm_bls12381_g1_multiexp", "gmsm_bls12381_g2_multiexp", "gmsm_bls12377_g1_multiexp", "gmsm_bls12377_g2_multiexp",
     "gmsm_secp256k1_g1_multiexp", "gmsm_bw6761_g1_multiexp", "gmsm_bw6761_g2_multiexp",
+    "gmsm_bls24315_g1_multiexp", "gmsm_bls24317_g1_multiexp", "gmsm_bw6633_g1_multiexp", "gmsm_bw6633_g2_multiexp",
     "gmsm_multiexp", "gmsm_choose_window_bits", "gmsm_multiexp_window_sums", "gmsm_last_oneshot_launches", "gmsm_bases_upload", "gmsm_bases_multiexp", "gmsm_bases_multiexp_device", "gmsm_bases_free",
     "gmsm_bases_precompute", "gmsm_bases_table_bits", "gmsm_ctx_create_tables", "gmsm_tables_build_device", "gmsm_ctx_msm_tables_device",
     "gmsm_ctx_create", "gmsm_ctx_destroy", "gmsm_ctx_window_bits", "gmsm_ctx_num_windows", "gmsm_ctx_workspace_bytes",
@@ -51,7 +52,8 @@ def lib() -> ctypes.CDLL:
         getattr(L, f).argtypes = [i32]
     for f in ("gmsm_bn254_g1_multiexp", "gmsm_bn254_g2_multiexp", "gmsm_bls12381_g1_multiexp", "gmsm_bls12381_g2_multiexp",
               "gmsm_bls12377_g1_multiexp", "gmsm_bls12377_g2_multiexp", "gmsm_secp256k1_g1_multiexp", "gmsm_bw6761_g1_multiexp",
-              "gmsm_bw6761_g2_multiexp"):
+              "gmsm_bw6761_g2_multiexp", "gmsm_bls24315_g1_multiexp", "gmsm_bls24317_g1_multiexp", "gmsm_bw6633_g1_multiexp",
+              "gmsm_bw6633_g2_multiexp"):
         getattr(L, f).argtypes = [vp, vp, sz, i32, vp]
     L.gmsm_multiexp.argtypes = [i32, vp, vp, sz, i32, vp]
     L.gmsm_choose_window_bits.argtypes = [i32, sz]

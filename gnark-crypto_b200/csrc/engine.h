@@ -135,6 +135,6 @@ struct GroupVTable {
   int (*table_level)(const void* d_in, size_t n, int c, void* d_out, cudaStream_t);   // out[i] = 2^c * in[i]
 };
 extern const GroupVTable vt_bn254_g1, vt_bn254_g2, vt_bls12381_g1, vt_bls12381_g2, vt_bls12377_g1, vt_bls12377_g2, vt_secp256k1_g1,
-    vt_bw6761_g1, vt_bw6761_g2;
+    vt_bw6761_g1, vt_bw6761_g2, vt_bls24315_g1, vt_bls24317_g1, vt_bw6633_g1, vt_bw6633_g2;
 
 }  // namespace gmsm

@@ -57,6 +57,10 @@ static bool curve_info(int curve, CurveInfo* ci) {
     case GMSM_SECP256K1_G1: *ci = {secp256k1_g1::F::N, secp256k1_fr::BITS, 4 * secp256k1_fr::N}; return true;
     case GMSM_BW6761_G1: *ci = {bw6761_g1::F::N, bw6761_fr::BITS, 4 * bw6761_fr::N}; return true;
     case GMSM_BW6761_G2: *ci = {bw6761_g2::F::N, bw6761_fr::BITS, 4 * bw6761_fr::N}; return true;
+    case GMSM_BLS24315_G1: *ci = {bls24315_g1::F::N, bls24315_fr::BITS, 4 * bls24315_fr::N}; return true;
+    case GMSM_BLS24317_G1: *ci = {bls24317_g1::F::N, bls24317_fr::BITS, 4 * bls24317_fr::N}; return true;
+    case GMSM_BW6633_G1: *ci = {bw6633_g1::F::N, bw6633_fr::BITS, 4 * bw6633_fr::N}; return true;
+    case GMSM_BW6633_G2: *ci = {bw6633_g2::F::N, bw6633_fr::BITS, 4 * bw6633_fr::N}; return true;
   }
   return false;
 }
@@ -77,6 +81,10 @@ static const GroupVTable* vtable(int curve) {
     case GMSM_SECP256K1_G1: return &vt_secp256k1_g1;
     case GMSM_BW6761_G1: return &vt_bw6761_g1;
     case GMSM_BW6761_G2: return &vt_bw6761_g2;
+    case GMSM_BLS24315_G1: return &vt_bls24315_g1;
+    case GMSM_BLS24317_G1: return &vt_bls24317_g1;
+    case GMSM_BW6633_G1: return &vt_bw6633_g1;
+    case GMSM_BW6633_G2: return &vt_bw6633_g2;
   }
   return nullptr;
 }
@@ -112,9 +120,14 @@ static const WidthModel& width_model(int curve) {
   // (512 buckets).  bw6-761: the 377 doublings of the 24-limb Horner chain alone are ~9 ms.
   static const WidthModel secp256k1_g1 = {0.1755, {2.50, 2.50, 2.95, 3.08, 3.45, 4.17, 7.66}, 2.05, 3.30};
   static const WidthModel bw6761 = {1.63, {16.8, 16.5, 17.7, 19.3, 25.9, 30.2, 46.6}, 13.2, 33.4};
+  // 10- and 20-limb groups: scaled from the neighbouring measured groups by the multiplier work (N^2), to be refitted
+  static const WidthModel bls24_g1 = {0.26, {3.9, 3.9, 3.3, 3.4, 4.1, 5.3, 7.4}, 0, 0};
+  static const WidthModel bw6633 = {1.10, {11.5, 11.3, 12.1, 13.2, 17.7, 20.6, 31.8}, 9.0, 22.8};
   switch (curve) {
     case GMSM_SECP256K1_G1: return secp256k1_g1;
     case GMSM_BW6761_G1: case GMSM_BW6761_G2: return bw6761;
+    case GMSM_BLS24315_G1: case GMSM_BLS24317_G1: return bls24_g1;
+    case GMSM_BW6633_G1: case GMSM_BW6633_G2: return bw6633;
     case GMSM_BN254_G1: return bn254_g1;
     case GMSM_BLS12381_G1: case GMSM_BLS12377_G1: return bls_g1;
     case GMSM_BN254_G2: return bn254_g2;
@@ -150,7 +163,7 @@ static int choose_c_for(int curve, int fr_bits, size_t n) {
   return bc;
 }
 static int curve_of_bits_default(int fr_bits) {
-  return fr_bits == 254 ? GMSM_BN254_G1 : fr_bits == 255 ? GMSM_BLS12381_G1 : fr_bits == 256 ? GMSM_SECP256K1_G1 : fr_bits == 377 ? GMSM_BW6761_G1 : GMSM_BLS12377_G1;
+  return fr_bits == 254 ? GMSM_BN254_G1 : fr_bits == 255 ? GMSM_BLS12381_G1 : fr_bits == 256 ? GMSM_SECP256K1_G1 : fr_bits == 377 ? GMSM_BW6761_G1 : fr_bits == 315 ? GMSM_BW6633_G1 : GMSM_BLS12377_G1;
 }
 static int choose_c(int fr_bits, size_t n) { return choose_c_for(curve_of_bits_default(fr_bits), fr_bits, n); }
 
@@ -1214,6 +1227,10 @@ extern "C" int gmsm_bls12377_g2_multiexp(const uint64_t* p, const uint64_t* s, s
 extern "C" int gmsm_secp256k1_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[12]) { return gmsm_multiexp(GMSM_SECP256K1_G1, p, s, n, t, out); }
 extern "C" int gmsm_bw6761_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BW6761_G1, p, s, n, t, out); }
 extern "C" int gmsm_bw6761_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[36]) { return gmsm_multiexp(GMSM_BW6761_G2, p, s, n, t, out); }
+extern "C" int gmsm_bls24315_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[15]) { return gmsm_multiexp(GMSM_BLS24315_G1, p, s, n, t, out); }
+extern "C" int gmsm_bls24317_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[15]) { return gmsm_multiexp(GMSM_BLS24317_G1, p, s, n, t, out); }
+extern "C" int gmsm_bw6633_g1_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[30]) { return gmsm_multiexp(GMSM_BW6633_G1, p, s, n, t, out); }
+extern "C" int gmsm_bw6633_g2_multiexp(const uint64_t* p, const uint64_t* s, size_t n, int t, uint64_t out[30]) { return gmsm_multiexp(GMSM_BW6633_G2, p, s, n, t, out); }
 
 // ------------------------------------------------------------------------------------------
 // base generator

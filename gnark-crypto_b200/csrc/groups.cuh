@@ -37,6 +37,12 @@ using bls12377_g2 = GroupT<5, bls12377_fp, bls12377_fr, true>;   // Fp2 with u^2
 using secp256k1_g1 = GroupT<6, secp256k1_fp, secp256k1_fr, false>;
 using bw6761_g1 = GroupT<7, bw6761_fp, bw6761_fr, false>;
 using bw6761_g2 = GroupT<8, bw6761_fp, bw6761_fr, false>;
+// bls24-315 / bls24-317 G1 (5-word Fp = 10 limbs; G2 of these curves is over Fp4: not on this path), bw6-633 G1 / G2 (10-word Fp,
+// both groups over Fp; fr = 5 words, 315 bits: 40-byte scalars)
+using bls24315_g1 = GroupT<9, bls24315_fp, bls24315_fr, false>;
+using bls24317_g1 = GroupT<10, bls24317_fp, bls24317_fr, false>;
+using bw6633_g1 = GroupT<11, bw6633_fp, bw6633_fr, false>;
+using bw6633_g2 = GroupT<12, bw6633_fp, bw6633_fr, false>;
 
 // word (u32) counts
 template <class G> constexpr int coord_words() { return G::F::N; }

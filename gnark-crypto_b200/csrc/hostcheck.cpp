@@ -40,10 +40,18 @@ using HcG = secp256k1_g1;
 using HcG = bw6761_g1;
 #elif HC_GROUP == 8
 using HcG = bw6761_g2;
+#elif HC_GROUP == 9
+using HcG = bls24315_g1;
+#elif HC_GROUP == 10
+using HcG = bls24317_g1;
+#elif HC_GROUP == 11
+using HcG = bw6633_g1;
+#elif HC_GROUP == 12
+using HcG = bw6633_g2;
 #else
 // field-only pseudo group: the secp256k1 SCALAR field as coordinate field, so that the stress vectors of the test reach the
 // second full-width modulus through the same multiplier (the engine itself only needs fromMont of it)
-using HcG = GroupT<9, secp256k1_fr, secp256k1_fr, false>;
+using HcG = GroupT<13, secp256k1_fr, secp256k1_fr, false>;
 #endif
 extern "C" int HC_CAT(hostcheck_op_, HC_GROUP)(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) {
   return run<HcG>(op, a, b, o, n);
@@ -68,7 +76,7 @@ extern "C" int HC_CAT(hostcheck_table_level_, HC_GROUP)(int c, const uint32_t* i
   return 0;
 }
 #else
-#define HC_FOR_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+#define HC_FOR_EACH(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 extern "C" {
 #define X(k) int hostcheck_op_##k(int, const uint32_t*, const uint32_t*, uint32_t*, size_t); \
   int hostcheck_table_level_##k(int, const uint32_t*, size_t, uint32_t*); \

@@ -23,21 +23,33 @@ namespace gmsm {
 static constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
 
 // ------------------------------------------------------------------------------------------
-// vector load / store of PODs made of uint32 limbs (size multiple of 16 B, 16 B aligned in memory)
+// vector load / store of PODs made of uint32 limbs: 16-byte granules where the size allows it (16 B aligned in memory), 8-byte
+// granules otherwise (the 10-limb fields of bls24-315 / bls24-317 / bw6-633: 40-byte elements and scalars, 120-byte Jacobian
+// triples -- a multiple of 8 and 8-byte aligned like every u64-limb object of the reference)
 // ------------------------------------------------------------------------------------------
 template <class T>
 GMSM_D T load_vec(const T* p) {
-  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  static_assert(sizeof(T) % 8 == 0, "8-byte granules");
   T r;
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-  const uint4* s = reinterpret_cast<const uint4*>(p);
+  if constexpr (sizeof(T) % 16 == 0) {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
-    uint4 v = s[i];
-    w[4 * i + 0] = v.x;
-    w[4 * i + 1] = v.y;
-    w[4 * i + 2] = v.z;
-    w[4 * i + 3] = v.w;
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
+      uint4 v = s[i];
+      w[4 * i + 0] = v.x;
+      w[4 * i + 1] = v.y;
+      w[4 * i + 2] = v.z;
+      w[4 * i + 3] = v.w;
+    }
+  } else {
+    const uint2* s = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); i++) {
+      uint2 v = s[i];
+      w[2 * i + 0] = v.x;
+      w[2 * i + 1] = v.y;
+    }
   }
   return r;
 }
@@ -46,7 +58,7 @@ GMSM_D T load_vec(const T* p) {
 // (ld.global.nc.v8.b32 -> LDG.E.256 on sm_100a); they are 32-byte aligned in device memory.
 template <class T>
 GMSM_D T load_vec_ro(const T* p) {
-  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  static_assert(sizeof(T) % 8 == 0, "8-byte granules");
   T r;
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
 #if defined(__CUDA_ARCH__)
@@ -61,7 +73,7 @@ GMSM_D T load_vec_ro(const T* p) {
     }
   } else
 #endif
-  {   // (also the whole function in the CPU emulation build of tests/emu/, which has no PTX)
+  if constexpr (sizeof(T) % 16 == 0) {   // (also the 32-byte multiples in the CPU emulation build of tests/emu/, which has no PTX)
     const uint4* s = reinterpret_cast<const uint4*>(p);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
@@ -71,16 +83,30 @@ GMSM_D T load_vec_ro(const T* p) {
       w[4 * i + 2] = v.z;
       w[4 * i + 3] = v.w;
     }
+  } else {
+    const uint2* s = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); i++) {
+      uint2 v = __ldg(s + i);
+      w[2 * i + 0] = v.x;
+      w[2 * i + 1] = v.y;
+    }
   }
   return r;
 }
 template <class T>
 GMSM_D void store_vec(T* p, const T& r) {
-  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  static_assert(sizeof(T) % 8 == 0, "8-byte granules");
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
-  uint4* d = reinterpret_cast<uint4*>(p);
+  if constexpr (sizeof(T) % 16 == 0) {
+    uint4* d = reinterpret_cast<uint4*>(p);
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  } else {
+    uint2* d = reinterpret_cast<uint2*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); i++) d[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+  }
 }
 
 // out-of-line copies of the rare / cold group operations keep the hot loops small (one mixed add is

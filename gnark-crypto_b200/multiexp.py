@@ -24,12 +24,15 @@ from . import _native
 
 CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5,
           # N4 remainder: ecc/secp256k1/multiexp.go:32 ; ecc/bw6-761/multiexp.go:32, :306 (G2 of bw6-761 is over Fp too)
-          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8}
+          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8,
+          # ecc/bls24-315/multiexp.go:32, ecc/bls24-317/multiexp.go:32 (G1 only: their G2 is over Fp4) ; ecc/bw6-633/multiexp.go:32, :304
+          "bls24315_g1": 9, "bls24317_g1": 10, "bw6633_g1": 11, "bw6633_g2": 12}
 # u64 words: (coordinate limbs L, coordinates per point-coordinate: 1 = Fp, 2 = Fp2)
-_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1), 5: (6, 2), 6: (4, 1), 7: (12, 1), 8: (12, 1)}
+_SHAPE = {0: (4, 1), 1: (4, 2), 2: (6, 1), 3: (6, 2), 4: (6, 1), 5: (6, 2), 6: (4, 1), 7: (12, 1), 8: (12, 1), 9: (5, 1), 10: (5, 1),
+          11: (10, 1), 12: (10, 1)}
 # fr.Limbs / fr.Bits of each curve id: a scalar is SCALAR_WORDS x uint64 in Montgomery form
-SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6}
-SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377}
+SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6, 9: 4, 10: 4, 11: 5, 12: 5}
+SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377, 9: 253, 10: 255, 11: 315, 12: 315}
 
 
 class MultiExpError(Exception):
@@ -141,8 +144,8 @@ class _AffBase(_Point):
 
 
 def curve_package(curve: str):
-    """Returns (G1Affine, G1Jac, G2Affine, G2Jac) bound to `curve` in {"bn254", "bls12381", "bls12377", "secp256k1", "bw6761"}
-    -- the analogue of importing ecc/bn254, ecc/bls12-381, ... (secp256k1 has no G2: None, None)."""
+    """Returns (G1Affine, G1Jac, G2Affine, G2Jac) bound to `curve` in {"bn254", "bls12381", "bls12377", "secp256k1", "bw6761", "bls24315", "bls24317", "bw6633"}
+    -- the analogue of importing ecc/bn254, ecc/bls12-381, ... (no G2 for secp256k1; none provided for bls24-315 / bls24-317: None, None)."""
     out = []
     for grp in ("g1", "g2"):
         if "%s_%s" % (curve, grp) not in CURVES:   # secp256k1: G1 only

@@ -13,9 +13,9 @@
  * sibling of the generated multiexp.go.  Buffers are passed exactly as Go holds them:
  *
  *   points  : n x {X, Y}; each coordinate L little-endian uint64 limbs in Montgomery form
- *             (L = 4 bn254 / secp256k1, 6 bls12-381 / bls12-377, 12 bw6-761; G2 coordinates are {A0, A1} pairs, except on
- *             bw6-761 whose G2 is over Fp); infinity = all zero (g1.go:41-47,178-180).  64 / 96 / 128 / 192 bytes per point.
- *   scalars : n x fr.Limbs uint64 (4; 6 for bw6-761 -- gmsm_scalar_bytes), Montgomery form, reduced (fr/element.go:36).
+ *             (L = 4 bn254 / secp256k1, 5 bls24-315 / bls24-317, 6 bls12-381 / bls12-377, 10 bw6-633, 12 bw6-761; G2 coordinates are {A0, A1} pairs, except on
+ *             bw6-761 / bw6-633 whose G2 is over Fp); infinity = all zero (g1.go:41-47,178-180).  64 / 96 / 128 / 192 bytes per point.
+ *   scalars : n x fr.Limbs uint64 (4; 5 for bw6-633, 6 for bw6-761 -- gmsm_scalar_bytes), Montgomery form, reduced (fr/element.go:36).
  *   out     : Jacobian {X, Y, Z}, 3 x L (G2: 3 x 2L) uint64, Montgomery form.  The engine writes the
  *             affine-normalised representative (X, Y, One), or (0, 0, 0) for infinity.  It is
  *             G1Jac.Equal to what the Go path returns and FromJacobian of it is limb-identical.
@@ -44,7 +44,11 @@ typedef enum {
   GMSM_BLS12377_G2 = 5,  /* its Fp2 tower has u^2 = -5 (e2_bls377.go) */
   GMSM_SECP256K1_G1 = 6, /* N4: ecc/secp256k1/multiexp.go:32 -- fp and fr fill all 256 bits */
   GMSM_BW6761_G1 = 7,    /* N4: ecc/bw6-761/multiexp.go:32  -- 12-word Fp, scalars are 6 x uint64 (fr.Bits = 377) */
-  GMSM_BW6761_G2 = 8     /* N4: ecc/bw6-761/multiexp.go:306 -- G2 is also over Fp */
+  GMSM_BW6761_G2 = 8,    /* N4: ecc/bw6-761/multiexp.go:306 -- G2 is also over Fp */
+  GMSM_BLS24315_G1 = 9,  /* N4: ecc/bls24-315/multiexp.go:32 -- 5-word Fp (G2 of the bls24 curves is over Fp4: not provided) */
+  GMSM_BLS24317_G1 = 10, /* N4: ecc/bls24-317/multiexp.go:32 */
+  GMSM_BW6633_G1 = 11,   /* N4: ecc/bw6-633/multiexp.go:32  -- 10-word Fp, scalars are 5 x uint64 (fr.Bits = 315) */
+  GMSM_BW6633_G2 = 12    /* N4: ecc/bw6-633/multiexp.go:304 -- G2 over Fp */
 } gmsm_curve_t;
 
 enum {
@@ -85,6 +89,14 @@ int gmsm_bw6761_g1_multiexp(const uint64_t* points, const uint64_t* scalars /* n
                             uint64_t out_jac[36]);     /* ecc/bw6-761/multiexp.go:32 */
 int gmsm_bw6761_g2_multiexp(const uint64_t* points, const uint64_t* scalars /* n x 6 */, size_t n, int nb_tasks,
                             uint64_t out_jac[36]);     /* ecc/bw6-761/multiexp.go:306 (G2 is over Fp as well) */
+int gmsm_bls24315_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[15]);   /* ecc/bls24-315/multiexp.go:32 */
+int gmsm_bls24317_g1_multiexp(const uint64_t* points, const uint64_t* scalars, size_t n, int nb_tasks,
+                              uint64_t out_jac[15]);   /* ecc/bls24-317/multiexp.go:32 */
+int gmsm_bw6633_g1_multiexp(const uint64_t* points, const uint64_t* scalars /* n x 5 */, size_t n, int nb_tasks,
+                            uint64_t out_jac[30]);     /* ecc/bw6-633/multiexp.go:32 */
+int gmsm_bw6633_g2_multiexp(const uint64_t* points, const uint64_t* scalars /* n x 5 */, size_t n, int nb_tasks,
+                            uint64_t out_jac[30]);     /* ecc/bw6-633/multiexp.go:304 */
 int gmsm_multiexp(gmsm_curve_t curve, const uint64_t* points, const uint64_t* scalars, size_t n,
                   int nb_tasks, uint64_t* out_jac);
 /* sharded calls with one process per GPU: every process runs its shard through the pipelined engine and gets the W

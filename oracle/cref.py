@@ -13,10 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libmsmref.so")
 
 CURVES = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3, "bls12377_g1": 4, "bls12377_g2": 5,
-          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8}
-AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12, 5: 24, 6: 8, 7: 24, 8: 24}  # u64 words per affine point
-SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6}      # u64 words per scalar (fr.Limbs)
-SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377}   # fr.Bits
+          "secp256k1_g1": 6, "bw6761_g1": 7, "bw6761_g2": 8, "bls24315_g1": 9, "bls24317_g1": 10, "bw6633_g1": 11, "bw6633_g2": 12}
+AFF_WORDS = {0: 8, 1: 16, 2: 12, 3: 24, 4: 12, 5: 24, 6: 8, 7: 24, 8: 24, 9: 10, 10: 10, 11: 20, 12: 20}  # u64 words per affine point
+SCALAR_WORDS = {0: 4, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 6, 8: 6, 9: 4, 10: 4, 11: 5, 12: 5}      # u64 words per scalar (fr.Limbs)
+SCALAR_BITS = {0: 254, 1: 254, 2: 255, 3: 255, 4: 253, 5: 253, 6: 256, 7: 377, 8: 377, 9: 253, 10: 255, 11: 315, 12: 315}   # fr.Bits
 
 _lib = None
 
@@ -135,7 +135,7 @@ def field_op(field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
     out = np.zeros_like(a)
-    L = {2: 6, 4: 6, 8: 12, 9: 6}.get(field, 4)
+    L = {2: 6, 4: 6, 8: 12, 9: 6, 10: 5, 12: 5, 14: 10, 15: 5}.get(field, 4)
     rc = lib().ref_field_op(field, op, _p(a), _p(b), _p(out), a.size // L)
     if rc != 0:
         raise RuntimeError("ref_field_op rc=%d" % rc)

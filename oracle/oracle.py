@@ -191,6 +191,13 @@ FIELDS = {
              rsquare=[13224372171368877346, 227991066186625457, 2496666625421784173, 13825906835078366124, 9475172226622360569,
                       30958721782860680]),
     ),
+    # N4: ecc/bls24-315/fp/element.go:31,73 fr:31,71 ; ecc/bls24-317/fp:31,73 fr:31,71 ; ecc/bw6-633/fp:31,83 fr:31,73 (qInvNeg, rSquare pins)
+    "bls24315_fp": Field("bls24315_fp", 0x4C23A02B586D650D3F7498BE97C5EAFDEC1D01AA27A1AE0421EE5DA52BDE5026FE802FF40300001, 5, dict(qinvneg=8083954730842193919, rsquare=[7746605402484284438, 6457291528853138485, 14067144135019420374, 14705958577488011058, 150264569250089173])),
+    "bls24315_fr": Field("bls24315_fr", 0x196DEAC24A9DA12B25FC7EC9CF927A98C8C480ECE644E36419D0C5FD00C00001, 4, dict(qinvneg=2184305180030271487, rsquare=[6242551132904523857, 16951295617263545407, 10923821274252739203, 584663452775307866])),
+    "bls24317_fp": Field("bls24317_fp", 0x1058CA226F60892CF28FC5A0B7F9D039169A61E684C73446D6F339E43424BF7E8D512E565DAB2AAB, 5, dict(qinvneg=6176088765535387645, rsquare=[8184925746953654484, 11847028797714522427, 6382817893761672566, 4341726315782040335, 1146553493836047074])),
+    "bls24317_fr": Field("bls24317_fr", 0x443F917EA68DAFC2D0B097F28D83CD491CD1E79196BF0E7AF000000000000001, 4, dict(qinvneg=17293822569102704639, rsquare=[14966889745918050766, 10836803306611491707, 10398613988537905008, 4216292045776253362])),
+    "bw6633_fp": Field("bw6633_fp", 0x126633CC0F35F63FC1A174F01D72AB5A8FCD8C75D79D2C74E59769AD9BBDA2F8152A6C0FADEA490B8DA9F5E83F57C497E0E8850EDBDA407D7B5CE7AB839C2253D369BD31147F73CD74916EA4570000D, 10, dict(qinvneg=13046692460116554043, rsquare=[7358459907925294924, 14414180951914241931, 16619482658146888203, 760736596725344926, 12753071240931896792, 13425190760400245818, 12591714441439252728, 15325516497554583360, 5301152003049442834, 35368377961363834])),
+    "bw6633_fr": Field("bw6633_fr", 0x4C23A02B586D650D3F7498BE97C5EAFDEC1D01AA27A1AE0421EE5DA52BDE5026FE802FF40300001, 5, dict(qinvneg=8083954730842193919, rsquare=[7746605402484284438, 6457291528853138485, 14067144135019420374, 14705958577488011058, 150264569250089173])),
 }
 
 
@@ -640,13 +647,31 @@ def _mk_groups():
             562923658089539719386922163444547387757586534741080263946953401595155211934630598999300396317104182598044793758153214972605680357108252243146746187917218885078195819486220416605630144001533548163105316661692978285266378674355041,
         ),
     )
+    # ecc/bls24-315/bls24-315.go:105-113 (Y^2 = X^3 + 1), ecc/bls24-317/bls24-317.go:91-99 (Y^2 = X^3 + 4): G1 only -- G2 of the
+    # bls24 curves is defined over Fp4 and is not on this path
+    g["bls24315_g1"] = Group("bls24315_g1", FpOps(FIELDS["bls24315_fp"]), FIELDS["bls24315_fr"], 1, (
+        34223510504517033132712852754388476272837911830964394866541204856091481856889569724484362330263,
+        24215295174889464585413596429561903295150472552154479431771837786124301185073987899223459122783))
+    g["bls24317_g1"] = Group("bls24317_g1", FpOps(FIELDS["bls24317_fp"]), FIELDS["bls24317_fr"], 4, (
+        26261810162995192444253184251590159762050205376519976412461726336843100448942248976252388876791,
+        26146603602820658047261036676090398397874822703333117264049387703172159980214065566219085800243))
+    # ecc/bw6-633/bw6-633.go:82-93 : G1 Y^2 = X^3 + 4, M-twist G2 Y^2 = X^3 + 8, both over the 10-word Fp; fr = 5 words, 315 bits
+    K = FpOps(FIELDS["bw6633_fp"])
+    g["bw6633_g1"] = Group("bw6633_g1", K, FIELDS["bw6633_fr"], 4, (
+        14087405796052437206213362229855313116771222912153372774869400386285407949123477431442535997951698710614498307938219633856996133201713506830167161540335446217605918678317160130862890417553415,
+        5208886161111258314476333487866604447704068601830026647530443033297117148121067806438008469463787158470000157308702133756065259580313172904438248825389121766442385979570644351664733475122746))
+    g["bw6633_g2"] = Group("bw6633_g2", K, FIELDS["bw6633_fr"], 8, (
+        13658793733252505713431834233072715040674666715141692574468286839081203251180283741830175712695426047062165811313478642863696265647598838732554425602399576125615559121457137320131899043374497,
+        599560264833409786573595720823495699033661029721475252751314180543773745554433461106678360045466656230822473390866244089461950086268801746497554519984580043036179195728559548424763890207250))
     return g
 
 
 GROUPS = _mk_groups()
 
 # implementedCs of each curve's MultiExp (multiexp.go:77): what bestC may return
-IMPLEMENTED_CS = {"secp256k1_g1": tuple(range(4, 16)), "bw6761_g1": (4, 5, 8, 10, 16), "bw6761_g2": (4, 5, 8, 10, 16)}
+IMPLEMENTED_CS = {"secp256k1_g1": tuple(range(4, 16)), "bw6761_g1": (4, 5, 8, 10, 16), "bw6761_g2": (4, 5, 8, 10, 16),
+                  "bls24315_g1": tuple(range(4, 17)), "bls24317_g1": tuple(range(4, 17)), "bw6633_g1": (4, 5, 6, 8, 12, 16),
+                  "bw6633_g2": (4, 5, 6, 8, 12, 16)}
 
 
 # --------------------------------------------------------------------------------------

@@ -310,7 +310,7 @@ int emu_finalize(const void* partials, int nranks, int c, int tables, void* out_
 }  // namespace
 
 #ifndef EMU_GROUP
-#error "compile with -DEMU_GROUP=0..8"
+#error "compile with -DEMU_GROUP=0..12"
 #endif
 #if EMU_GROUP == 0
 using EmuG = bn254_g1;
@@ -328,8 +328,16 @@ using EmuG = bls12377_g2;
 using EmuG = secp256k1_g1;
 #elif EMU_GROUP == 7
 using EmuG = bw6761_g1;
-#else
+#elif EMU_GROUP == 8
 using EmuG = bw6761_g2;
+#elif EMU_GROUP == 9
+using EmuG = bls24315_g1;
+#elif EMU_GROUP == 10
+using EmuG = bls24317_g1;
+#elif EMU_GROUP == 11
+using EmuG = bw6633_g1;
+#else
+using EmuG = bw6633_g2;
 #endif
 #define EMU_CAT2(a, b) a##b
 #define EMU_CAT(a, b) EMU_CAT2(a, b)

@@ -30,9 +30,9 @@ def test_sizes_match_go_layout():
     pkg = _pkg()
     L = pkg._native.lib()
     # affine 64 / 128 / 96 / 192 B, scalars 32 B, Jacobian 96 / 192 / 144 / 288 B
-    assert [L.gmsm_affine_bytes(c) for c in range(9)] == [64, 128, 96, 192, 96, 192, 64, 192, 192]
-    assert [L.gmsm_scalar_bytes(c) for c in range(9)] == [32] * 7 + [48, 48]     # bw6-761: fr.Limbs = 6
-    assert L.gmsm_affine_bytes(9) == 0 and L.gmsm_scalar_bytes(9) == 0
+    assert [L.gmsm_affine_bytes(c) for c in range(13)] == [64, 128, 96, 192, 96, 192, 64, 192, 192, 80, 80, 160, 160]
+    assert [L.gmsm_scalar_bytes(c) for c in range(13)] == [32] * 7 + [48, 48, 32, 32, 40, 40]     # bw6-761: fr.Limbs = 6, bw6-633: 5
+    assert L.gmsm_affine_bytes(13) == 0 and L.gmsm_scalar_bytes(13) == 0
     assert [L.gmsm_jac_bytes(c) for c in range(4)] == [96, 192, 144, 288]
     assert [L.gmsm_xyzz_bytes(c) for c in range(4)] == [128, 256, 192, 384]
     assert b"sm_100a" in L.gmsm_version()

@@ -8,7 +8,8 @@ from oracle import cref
 from oracle import oracle as O
 
 FIELD_IDS = {"bn254_fp": 0, "bn254_fr": 1, "bls12381_fp": 2, "bls12381_fr": 3, "bls12377_fp": 4, "bls12377_fr": 5,
-             "secp256k1_fp": 6, "secp256k1_fr": 7, "bw6761_fp": 8, "bw6761_fr": 9}
+             "secp256k1_fp": 6, "secp256k1_fr": 7, "bw6761_fp": 8, "bw6761_fr": 9, "bls24315_fp": 10, "bls24315_fr": 11,
+             "bls24317_fp": 12, "bls24317_fr": 13, "bw6633_fp": 14, "bw6633_fr": 15}
 
 
 def _limbs(f, vals):

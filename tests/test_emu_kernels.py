@@ -131,7 +131,8 @@ def test_emulated_kernels_skewed_inputs(kind, tables):
 
 
 @pytest.mark.parametrize("g,n", [("bn254_g2", 300), ("bls12381_g1", 400), ("bls12381_g2", 150), ("bls12377_g1", 300), ("bls12377_g2", 120),
-                                 ("secp256k1_g1", 400), ("bw6761_g1", 150), ("bw6761_g2", 120)])
+                                 ("secp256k1_g1", 400), ("bw6761_g1", 150), ("bw6761_g2", 120), ("bls24315_g1", 300), ("bls24317_g1", 300),
+                                 ("bw6633_g1", 150), ("bw6633_g2", 120)])
 def test_emulated_kernels_other_groups(g, n):
     pts, s = make_inputs(g, n, 99)
     want, _, _, _ = cref.msm(g, pts, s, c=0, nthreads=4)

@@ -3,7 +3,11 @@
     layer's carry-aware path runs (field.cuh Params::FULL) and a 16-bit window needs 17-bit digits in the last window
     (fr.Bits = 256 is a multiple of 16; the reference leaves c = 16 out of implementedCs for this curve, multiexp.go:77);
   * bw6-761 G1 and G2 (ecc/bw6-761/multiexp.go:32, :306) -- 12-word Fp (24 32-bit limbs per coordinate), BOTH groups
-    over Fp, scalars of 6 words / 377 bits (48-byte fr.Element: every scalar stride of the C ABI is per curve).
+    over Fp, scalars of 6 words / 377 bits (48-byte fr.Element: every scalar stride of the C ABI is per curve);
+  * bls24-315 / bls24-317 G1 (ecc/bls24-315/multiexp.go:32, ecc/bls24-317/multiexp.go:32) -- 5-word Fp: 40-byte coordinates,
+    80-byte points, 120-byte Jacobian results, i.e. sizes that are not multiples of 16 bytes (8-byte load / store granules);
+    G2 of these curves is over Fp4 and not provided;
+  * bw6-633 G1 and G2 (ecc/bw6-633/multiexp.go:32, :304) -- 10-word Fp, both groups over Fp, 5-word scalars (40 bytes).
 Same criteria as tests/test_gpu_msm.py: bit-exact affine limbs against the CPU oracle, through the C ABI."""
 from importlib import import_module
 
@@ -16,7 +20,7 @@ from tests.gpu_common import jac_to_affine_bytes, load_golden_msm, make_inputs
 
 pytestmark = pytest.mark.gpu
 
-N4 = ["secp256k1_g1", "bw6761_g1", "bw6761_g2"]
+N4 = ["secp256k1_g1", "bw6761_g1", "bw6761_g2", "bls24315_g1", "bls24317_g1", "bw6633_g1", "bw6633_g2"]
 
 
 def _pkg():
@@ -43,16 +47,22 @@ def _engine_msm(g, pts, s, c):
 def test_sizes_of_the_new_curves():
     L = import_module("gnark-crypto_b200._native").lib()
     pkg = _pkg()
-    for g, (ab, sb) in {"secp256k1_g1": (64, 32), "bw6761_g1": (192, 48), "bw6761_g2": (192, 48)}.items():
+    for g, (ab, sb) in {"secp256k1_g1": (64, 32), "bw6761_g1": (192, 48), "bw6761_g2": (192, 48), "bls24315_g1": (80, 32),
+                        "bls24317_g1": (80, 32), "bw6633_g1": (160, 40), "bw6633_g2": (160, 40)}.items():
         cid = pkg.CURVES[g]
         assert (L.gmsm_affine_bytes(cid), L.gmsm_scalar_bytes(cid), L.gmsm_jac_bytes(cid)) == (ab, sb, ab // 2 * 3)
         assert O.GROUPS[g].fr.limbs * 8 == sb
-    assert pkg.curve_package("secp256k1")[2:] == (None, None)           # no G2
+    for cv in ("secp256k1", "bls24315", "bls24317"):
+        assert pkg.curve_package(cv)[2:] == (None, None)                # no G2 (bls24: over Fp4, not provided)
 
 
 @pytest.mark.parametrize("g,n,cs", [("secp256k1_g1", 1500, [2, 4, 7, 8, 11, 13, 15, 16, 17, 19]),    # 16: last window 17 bits wide
                                      ("bw6761_g1", 500, [4, 5, 8, 10, 13, 16, 18]),                  # 13 * 29 = 377: last_c = 14
-                                     ("bw6761_g2", 400, [5, 10, 16])])
+                                     ("bw6761_g2", 400, [5, 10, 16]),
+                                     ("bls24315_g1", 1000, [2, 5, 8, 11, 13, 16, 19]),               # 253 = 11 * 23: last_c = 12
+                                     ("bls24317_g1", 1000, [3, 8, 15, 16, 17]),                      # 255 = 15 * 17: last windows of c + 1 bits
+                                     ("bw6633_g1", 600, [4, 5, 6, 7, 8, 9, 12, 15, 16, 18]),         # 315 = 5 * 63 = 7 * 45 = 9 * 35 = 15 * 21
+                                     ("bw6633_g2", 400, [6, 12, 16])])
 def test_window_sizes_agree_with_oracle(g, n, cs):
     """the widths the reference implements for the curve (multiexp.go:77) and the wider ones the GPU model may pick; inputs
     with the cross-test ingredients (infinities, duplicates, P / -P, zero scalars)"""
@@ -84,7 +94,7 @@ def test_committed_golden_vectors_and_one_shot_call(g):
     with pytest.raises(pkg.MultiExpError, match="len"):
         Jac().MultiExp(pts, s[:-1], pkg.MultiExpConfig())
     with pytest.raises(ValueError):
-        Jac().MultiExp(pts, np.zeros((pts.shape[0], 5), dtype=np.uint64), pkg.MultiExpConfig())   # wrong fr.Limbs
+        Jac().MultiExp(pts, np.zeros((pts.shape[0], s.shape[1] + 1), dtype=np.uint64), pkg.MultiExpConfig())   # wrong fr.Limbs
 
 
 @pytest.mark.parametrize("g", N4)
@@ -117,7 +127,8 @@ def test_infinity_zero_empty_and_extreme_scalars(g):
         assert np.array_equal(jac[: pts.shape[1]], want), c
 
 
-@pytest.mark.parametrize("g,n", [("secp256k1_g1", (1 << 19) + 11), ("bw6761_g1", (1 << 16) + 3), ("bw6761_g2", 1 << 15)])
+@pytest.mark.parametrize("g,n", [("secp256k1_g1", (1 << 19) + 11), ("bw6761_g1", (1 << 16) + 3), ("bw6761_g2", 1 << 15),
+                                 ("bls24315_g1", (1 << 18) + 7), ("bls24317_g1", 1 << 18), ("bw6633_g1", (1 << 17) + 1), ("bw6633_g2", 1 << 15)])
 def test_large_closed_form_and_host_paths(g, n):
     """bases [i+1]B generated on the device (pinned against the oracle on a sample), random scalars: the engine with its own
     window choice, the one-shot host call on pageable arrays (pinned staging ring; 48-byte scalars for bw6-761), resident
@@ -152,7 +163,7 @@ def test_large_closed_form_and_host_paths(g, n):
         rb.close()
 
 
-@pytest.mark.parametrize("g", ["secp256k1_g1", "bw6761_g1"])
+@pytest.mark.parametrize("g", ["secp256k1_g1", "bw6761_g1", "bls24317_g1", "bw6633_g1"])
 @pytest.mark.parametrize("kind", ["smallvalues", "redundancy", "one_bucket"])
 def test_skewed_scalar_distributions(g, kind):
     """multiexp_test.go:319-334's distributions: both modes of the counting sort and the carry levels with the new strides"""
@@ -194,7 +205,7 @@ def test_sharded_window_sums_compose_bw6761():
         eng.close()
 
 
-@pytest.mark.parametrize("g", ["secp256k1_g1", "bw6761_g2"])
+@pytest.mark.parametrize("g", ["secp256k1_g1", "bw6761_g2", "bls24315_g1", "bw6633_g1"])
 def test_batch_scalar_multiplication_fixed_base(g):
     """BatchScalarMultiplicationG1 (ecc/secp256k1/g1.go, ecc/bw6-761/g2.go): same base, n scalars, affine out"""
     pkg = _pkg()

@@ -36,7 +36,7 @@ def _build(variant):
                                                      "emulated_dot4": ["-DGMSM_EMULATE_PTX", "-DGMSM_SQR_DEDICATED=1", "-DGMSM_DOT2=1", "-DGMSM_FP2_DOT2=1", "-DGMSM_DOT4=1"]}[variant]
             src = os.path.join(CSRC, "hostcheck.cpp")
             objs, procs = [], []
-            for k in list(range(len(O.GROUPS) + 1)) + [None]:     # + the field-only pseudo group 9 (secp256k1 fr)
+            for k in list(range(len(O.GROUPS) + 1)) + [None]:     # + the field-only pseudo group (secp256k1 fr)
                 o = os.path.join(bdir, "hostcheck%s_%s.o" % (tag, "d" if k is None else k))
                 objs.append(o)
                 procs.append(subprocess.Popen(["g++", *flags, *([] if k is None else ["-DHC_GROUP=%d" % k]), "-c", "-o", o, src]))
@@ -64,9 +64,9 @@ def hc(request):
 
 
 def _runner(hc, g):
-    cid = 9 if g == "secp256k1_fr" else list(O.GROUPS).index(g)
+    cid = len(O.GROUPS) if g == "secp256k1_fr" else list(O.GROUPS).index(g)
     assert list(O.GROUPS) == ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2", "bls12377_g1", "bls12377_g2", "secp256k1_g1",
-                              "bw6761_g1", "bw6761_g2"]
+                              "bw6761_g1", "bw6761_g2", "bls24315_g1", "bls24317_g1", "bw6633_g1", "bw6633_g2"]
 
     def run(op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)
@@ -93,7 +93,8 @@ def test_point_ops_host(hc, g):
 
 
 @pytest.mark.parametrize("g,c", [("bn254_g1", 5), ("bn254_g1", 22), ("bn254_g2", 7), ("bls12381_g1", 11), ("bls12381_g2", 3),
-                                 ("bls12377_g1", 9), ("bls12377_g2", 4), ("secp256k1_g1", 8), ("bw6761_g1", 6), ("bw6761_g2", 5)])
+                                 ("bls12377_g1", 9), ("bls12377_g2", 4), ("secp256k1_g1", 8), ("bw6761_g1", 6), ("bw6761_g2", 5),
+                                 ("bls24315_g1", 7), ("bls24317_g1", 10), ("bw6633_g1", 6), ("bw6633_g2", 9)])
 def test_table_level_host(hc, g, c):
     """one level of the window tables (k_table_level's batch function, built for the CPU): out_i = 2^c * in_i in affine
     normal form, infinity preserved, ragged batch (19 = 2 full batches of 8 + 3)"""
@@ -119,7 +120,7 @@ def test_table_level_host(hc, g, c):
 
 def test_window_plan(hc):
     buf = (ctypes.c_int * 6)()
-    for bits in (253, 254, 255, 256, 377):
+    for bits in (253, 254, 255, 256, 315, 377):
         for c in range(2, 25):
             hc.hostcheck_plan(bits, c, buf)
             W = O.compute_nb_chunks(bits, c)
@@ -127,7 +128,8 @@ def test_window_plan(hc):
             assert list(buf) == [c, W, lc, 1 << (c - 1), 1 << (lc - 1), (W - 1) * (1 << (c - 1)) + (1 << (lc - 1))]
 
 
-@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1", "secp256k1_g1", "secp256k1_fr", "bw6761_g1"])
+@pytest.mark.parametrize("g", ["bn254_g1", "bls12381_g1", "bls12377_g1", "secp256k1_g1", "secp256k1_fr", "bw6761_g1", "bls24315_g1",
+                               "bls24317_g1", "bw6633_g1"])
 def test_carry_chain_mul_sqr_stress(g):
     """the device formulation of Mul / Square (emulated) against the portable path and big-int arithmetic on many random
     and extreme operands (limbs of all-ones, single bits, q-1, values next to the limb boundaries).  secp256k1's two moduli
@@ -158,7 +160,7 @@ def test_carry_chain_mul_sqr_stress(g):
     # the experimental fused two-product routine: (x*y + u*v) R^-1 with one reduction, against big-int arithmetic and
     # against its plain composition (two products and an addition) in the portable build
     C, D = A[rng.permutation(len(vals))], A[rng.permutation(len(vals))]
-    cid = 9 if g == "secp256k1_fr" else list(O.GROUPS).index(g)
+    cid = len(O.GROUPS) if g == "secp256k1_fr" else list(O.GROUPS).index(g)
     outs = []
     for variant in ("portable", "emulated_sqr"):
         out = np.zeros_like(A)
