@@ -62,7 +62,7 @@ FR_Q = {
 
 def fr_mod(g):
     """the scalar-field modulus of a group"""
-    return FR_Q.get(g) or fr_mod(g)
+    return FR_Q.get(g) or FR_MOD[CURVE_BITS[g]]
 
 
 BASE_MULT = 0xC0FFEE            # the synthetic bases are [start + i] * B with B = [BASE_MULT] * generator

@@ -28,6 +28,12 @@ def test_synth_scalars_reduced_and_deterministic():
     from oracle import oracle as O
 
     assert b.FR_MOD[254] == O.FIELDS["bn254_fr"].q and b.FR_MOD[255] == O.FIELDS["bls12381_fr"].q and b.FR_MOD[253] == O.FIELDS["bls12377_fr"].q
+    # every group's scalar modulus, bit length, point size and scalar width as the oracle has them (bls24-315 / bls24-317 share
+    # their bit lengths with bls12-377 / bls12-381: looked up by group)
+    assert set(b.CURVE_BITS) == set(O.GROUPS)
+    for g, G in O.GROUPS.items():
+        assert b.fr_mod(g) == G.fr.q and b.CURVE_BITS[g] == G.fr.bits and b.scalar_words(b.CURVE_BITS[g]) == G.fr.limbs, g
+        assert b.AFF_BYTES[g] == 8 * G.aff_words, g
 
 
 def test_multiplier_pipe_accounting():
