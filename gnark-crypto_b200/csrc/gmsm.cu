@@ -325,7 +325,11 @@ static gmsm_ctx* ctx_create_ex(gmsm_curve_t curve, size_t max_n, int c, int devi
   // bw6-761 (24 limbs: one field product is ~9x bn254's, the serial Horner chain ~10 ms) takes them for the Horner / inversion
   // kernel and for small bucket reductions: 2^18 28.6 -> 27.3 ms, 2^14 17.3 -> 14.8 ms; large reductions stay one thread per
   // segment (2^22: 176.6 vs 186.0 ms with quads everywhere) -- profiles/r02_n4_new_curves_call12.txt
-  if (curve == GMSM_BW6761_G1 || curve == GMSM_BW6761_G2) { ctx->quad_mode = 1; ctx->quad_max_items = 20000; }
+  // (bw6-633, 20 limbs: 2^22 102.6 -> 101.5 ms, 2^18 18.2 -> 17.4 ms, profiles/r02_n4_model_checks_call14.txt)
+  if (curve == GMSM_BW6761_G1 || curve == GMSM_BW6761_G2 || curve == GMSM_BW6633_G1 || curve == GMSM_BW6633_G2) {
+    ctx->quad_mode = 1;
+    ctx->quad_max_items = 20000;
+  }
   if (const char* e = getenv("GMSM_QUAD")) { ctx->quad_mode = atoi(e); ctx->quad_max_items = (size_t)1 << 40; }
   if (const char* e = getenv("GMSM_QUAD_MAX")) { long v = atol(e); if (v >= 0) ctx->quad_max_items = (size_t)v; }
   if (const char* e = getenv("GMSM_SPLIT_W")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->split_w = ctx->split_tab = v; }

@@ -107,6 +107,9 @@ def test_window_model_choices_are_pinned():
     SECP, BW6_G1, BW6_G2 = 6, 7, 8
     want.update({(SECP, 16): 14, (SECP, 20): 16, (SECP, 22): 16, (SECP, 24): 20, (BW6_G1, 18): 14, (BW6_G1, 20): 16, (BW6_G1, 22): 18,
                  (BW6_G1, 24): 19, (BW6_G2, 20): 16})
+    # bls24-315 / bls24-317 G1, bw6-633 (profiles/r02_n4_more_curves_call13.txt, r02_n4_model_checks_call14.txt)
+    B315, B317, BW633_G1, BW633_G2 = 9, 10, 11, 12
+    want.update({(B315, 20): 17, (B315, 24): 20, (B317, 22): 17, (BW633_G1, 18): 15, (BW633_G1, 22): 18, (BW633_G2, 20): 16})
     for (curve, logn), c in want.items():
         assert L.gmsm_choose_window_bits(curve, 1 << logn) == c, (curve, logn)
     for curve in (BN_G1, BN_G2, BLS_G1, BLS_G2, BW6_G1):
