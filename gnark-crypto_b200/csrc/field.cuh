@@ -138,6 +138,29 @@ struct Fp {
   GMSM_HD bool operator!=(const Fp& b) const { return !(*this == b); }
 };
 
+// Modulus limb as a MULTIPLICAND.  Normally the generated constant (an immediate operand of IMAD.WIDE).  A modulus with
+// sparse limbs (bls12-377: 0x00000001, 0x8508c000, 0x30000000, ...) tempts ptxas into strength-reducing those products, which
+// splits the fused mad.lo.cc / madc.hi.cc pairs into IMAD.HI + IMAD.X -- two multiplier-pipe slots instead of one (measured:
+// bls12-377 G1 0.434 ns per mixed addition against bls12-381's 0.377 with identical source).  For such fields
+// (Params::MOD_IN_CONST_BANK) the multiplicand is read from __constant__ memory instead: a constant-bank operand costs no
+// register and hides the value from the optimiser.  Host builds and additive uses keep the immediate.
+template <class P>
+GMSM_HD uint32_t invm() {   // -q^-1 mod 2^32 as a multiplicand: see modm (for bls12-377 it is 0xffffffff, i.e. m = -t0)
+#if defined(__CUDA_ARCH__)
+  if constexpr (P::MOD_IN_CONST_BANK) return P::mod_cb(P::N);
+  else
+#endif
+  return P::INV;
+}
+template <class P>
+GMSM_HD uint32_t modm(int j) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (P::MOD_IN_CONST_BANK) return P::mod_cb(j);    // (generated next to the constants: a __constant__ array)
+  else
+#endif
+  return P::mod(j);
+}
+
 // r = (a >= q) ? a - q : a, for a value a + carry * 2^(32N) < 2q.  carry is always 0 for the moduli with a spare top bit
 // (2q < 2^(32N)); the full-width moduli (secp256k1 fp and fr, P::FULL) hand in the carry-out of the addition / the carry limb of
 // the multiplier: a - q then wraps to the right N limbs
@@ -331,23 +354,23 @@ GMSM_HD Fp<P> fp_mul_inline(const Fp<P>& x, const Fp<P>& y) {
     }
     Od[N] = 0;  // stale carry limb consumed by the shift
     // step 3
-    const uint32_t m = (Ev[0] + d) * P::INV;
+    const uint32_t m = (Ev[0] + d) * invm<P>();
     // step 4: Ev += q_even * m
-    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
-    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+    Ev[0] = mad_lo_cc(modm<P>(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(modm<P>(0), m, Ev[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
-      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+      Ev[j] = madc_lo_cc(modm<P>(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(modm<P>(j), m, Ev[j + 1]);
     }
     Ev[N] = addc(Ev[N], 0);
     // step 5: Od += q_odd * m  (no carry out)
-    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
-    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+    Od[0] = mad_lo_cc(modm<P>(1), m, Od[0]);
+    Od[1] = madc_hi_cc(modm<P>(1), m, Od[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
-      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+      Od[j] = madc_lo_cc(modm<P>(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(modm<P>(j + 1), m, Od[j + 1]);
     }
     if constexpr (P::FULL) Od[N] = addc(0, 0);
     e0prev = Ev[0];
@@ -465,21 +488,21 @@ GMSM_HD Fp<P> fp_sqr_inline(const Fp<P>& x) {
     if (chain) GMSM_NO_CARRY();
     Od[N] = 0;
     // steps 3-5: the reduction of fp_mul_inline, unchanged
-    const uint32_t m = (Ev[0] + d) * P::INV;
-    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
-    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+    const uint32_t m = (Ev[0] + d) * invm<P>();
+    Ev[0] = mad_lo_cc(modm<P>(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(modm<P>(0), m, Ev[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
-      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+      Ev[j] = madc_lo_cc(modm<P>(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(modm<P>(j), m, Ev[j + 1]);
     }
     Ev[N] = addc(Ev[N], 0);
-    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
-    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+    Od[0] = mad_lo_cc(modm<P>(1), m, Od[0]);
+    Od[1] = madc_hi_cc(modm<P>(1), m, Od[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
-      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+      Od[j] = madc_lo_cc(modm<P>(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(modm<P>(j + 1), m, Od[j + 1]);
     }
     GMSM_NO_CARRY();
     e0prev = Ev[0];
@@ -580,21 +603,21 @@ GMSM_HD Fp<P> fp_dot2_inline(const Fp<P>& x, const Fp<P>& y, const Fp<P>& u, con
     }
     GMSM_NO_CARRY();
     // steps 3-5: the reduction of fp_mul_inline, unchanged
-    const uint32_t m = (Ev[0] + d) * P::INV;
-    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
-    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+    const uint32_t m = (Ev[0] + d) * invm<P>();
+    Ev[0] = mad_lo_cc(modm<P>(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(modm<P>(0), m, Ev[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
-      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+      Ev[j] = madc_lo_cc(modm<P>(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(modm<P>(j), m, Ev[j + 1]);
     }
     Ev[N] = addc(Ev[N], 0);
-    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
-    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+    Od[0] = mad_lo_cc(modm<P>(1), m, Od[0]);
+    Od[1] = madc_hi_cc(modm<P>(1), m, Od[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
-      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+      Od[j] = madc_lo_cc(modm<P>(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(modm<P>(j + 1), m, Od[j + 1]);
     }
     GMSM_NO_CARRY();
     e0prev = Ev[0];
@@ -682,21 +705,21 @@ GMSM_HD Fp<P> fp_dot4_inline(const Fp<P>& x0, const Fp<P>& y0, const Fp<P>& x1, 
       }
     }
     // steps 3-5: the reduction of fp_mul_inline, unchanged
-    const uint32_t m = (Ev[0] + d) * P::INV;
-    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
-    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+    const uint32_t m = (Ev[0] + d) * invm<P>();
+    Ev[0] = mad_lo_cc(modm<P>(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(modm<P>(0), m, Ev[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
-      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+      Ev[j] = madc_lo_cc(modm<P>(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(modm<P>(j), m, Ev[j + 1]);
     }
     Ev[N] = addc(Ev[N], 0);
-    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
-    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+    Od[0] = mad_lo_cc(modm<P>(1), m, Od[0]);
+    Od[1] = madc_hi_cc(modm<P>(1), m, Od[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
-      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+      Od[j] = madc_lo_cc(modm<P>(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(modm<P>(j + 1), m, Od[j + 1]);
     }
     GMSM_NO_CARRY();
     e0prev = Ev[0];
@@ -910,21 +933,21 @@ GMSM_HD void fp_redc_half(const uint32_t* v, uint32_t* out) {
       for (int j = 0; j < N; j++) Od[j] = Od[j + 2];
       Od[N] = 0;
     }
-    const uint32_t m = (Ev[0] + d) * P::INV;
-    Ev[0] = mad_lo_cc(P::mod(0), m, Ev[0]);
-    Ev[1] = madc_hi_cc(P::mod(0), m, Ev[1]);
+    const uint32_t m = (Ev[0] + d) * invm<P>();
+    Ev[0] = mad_lo_cc(modm<P>(0), m, Ev[0]);
+    Ev[1] = madc_hi_cc(modm<P>(0), m, Ev[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Ev[j] = madc_lo_cc(P::mod(j), m, Ev[j]);
-      Ev[j + 1] = madc_hi_cc(P::mod(j), m, Ev[j + 1]);
+      Ev[j] = madc_lo_cc(modm<P>(j), m, Ev[j]);
+      Ev[j + 1] = madc_hi_cc(modm<P>(j), m, Ev[j + 1]);
     }
     Ev[N] = addc(Ev[N], 0);
-    Od[0] = mad_lo_cc(P::mod(1), m, Od[0]);
-    Od[1] = madc_hi_cc(P::mod(1), m, Od[1]);
+    Od[0] = mad_lo_cc(modm<P>(1), m, Od[0]);
+    Od[1] = madc_hi_cc(modm<P>(1), m, Od[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-      Od[j] = madc_lo_cc(P::mod(j + 1), m, Od[j]);
-      Od[j + 1] = madc_hi_cc(P::mod(j + 1), m, Od[j + 1]);
+      Od[j] = madc_lo_cc(modm<P>(j + 1), m, Od[j]);
+      Od[j + 1] = madc_hi_cc(modm<P>(j + 1), m, Od[j + 1]);
     }
     GMSM_NO_CARRY();
     e0prev = Ev[0];

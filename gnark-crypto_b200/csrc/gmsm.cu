@@ -108,17 +108,16 @@ struct WidthModel {
   double add_ns;          // accumulate: ns per mixed addition at c <= 17
   double tail_ms[7];      // tail_g(c) for c = 13 .. 19
   double fixed_ms;        // beyond c = 19: tail = fixed_ms + red19_ms * 2^(c - 19) (the bucket reduction doubles per bit, the carry
-  double red19_ms;        //   join / Horner / inversion do not); red19_ms = 0: the older rule tail_ms[6] * 2^(c - 19)
+  double red19_ms;        //   join / Horner / inversion do not; measured at c = 20, 21); red19_ms = 0: tail_ms[6] * 2^(c - 19)
 };
 static const WidthModel& width_model(int curve) {
-  static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}, 0, 0};
-  static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}, 0, 0};
-  static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}, 0, 0};
+  static const WidthModel bn254_g1 = {0.157, {2.56, 2.43, 2.19, 2.24, 2.41, 3.74, 6.30}, 1.7, 3.0};
+  static const WidthModel bls_g1 = {0.366, {5.29, 5.33, 4.42, 4.59, 5.75, 6.88, 8.53}, 2.85, 4.5};
+  static const WidthModel bn254_g2 = {0.509, {6.50, 6.37, 5.81, 5.95, 5.70, 9.30, 12.0}, 4.45, 6.67};
   static const WidthModel bls_g2 = {1.300, {13.6, 13.3, 12.2, 12.5, 12.0, 19.6, 25.2}, 0, 0};
   // N4 remainder: fitted from the width sweeps of profiles/r02_n4_new_curves_call11.txt / _call12.txt.  secp256k1: fr.Bits = 256
-  // makes the last window narrow for most widths (K1 contention, below); its c = 19 entry carries the measured 2 ms of that
-  // (512 buckets).  bw6-761: the 377 doublings of the 24-limb Horner chain alone are ~9 ms.
-  static const WidthModel secp256k1_g1 = {0.1755, {2.50, 2.50, 2.95, 3.08, 3.45, 4.17, 7.66}, 2.05, 3.30};
+  // makes the last window narrow for most widths (K1 contention, below).  bw6-761: the 377 doublings of the 24-limb Horner chain alone are ~9 ms.
+  static const WidthModel secp256k1_g1 = {0.1755, {2.50, 2.50, 2.95, 3.08, 3.45, 4.17, 5.66}, 2.05, 3.30};
   static const WidthModel bw6761 = {1.63, {16.8, 16.5, 17.7, 19.3, 25.9, 30.2, 46.6}, 13.2, 33.4};
   // 10- and 20-limb groups (bls24-315 / bls24-317 G1, bw6-633): fitted from profiles/r02_n4_more_curves_call13.txt; bw6-633's
   // c = 17 entry absorbs an accumulate that is 6 % slower per addition at that width than at 16 or 18
@@ -144,9 +143,12 @@ static double model_ms(int curve, int fr_bits, size_t n, int c) {
                                          : m.tail_ms[6] * (double)(1u << (c - 19));  // bucket reduction doubles per bit
   else tail = m.tail_ms[c - 13];
   // a narrow last window puts all its n entries on a handful of buckets: the histogram / rank atomics of K1 serialise on those
-  // addresses.  Measured on secp256k1 (fr.Bits = 256 = 16 * 16) at 2^24: +5.6 ms with 2 buckets (c = 15, 17), +2.7 ms with 16
-  // (c = 18), nothing at c = 16 (profiles/r02_n4_new_curves_call11.txt): ~0.4 / cbrt(buckets) ns per entry up to 256 buckets
-  if (p.nwin > 1 && p.nb_last <= 256) tail += 1e-6 * (double)n * 0.4 / std::cbrt((double)p.nb_last);
+  // addresses.  Measured at 2^24 (profiles/r02_n4_new_curves_call11.txt, r02_c20_checks_call15.txt): +5.6 ms with 2 buckets
+  // (secp256k1 c = 15, 17), +2.7 ms with 16 (c = 18), +3.8 ms with 64 (bls24-315 c = 19), +3.9 ms with 256 (bls12-381 c = 19),
+  // +2.0 ms with 512 (secp256k1 c = 19), nothing from 2^13 buckets on: 0.35 ns per entry up to 4 buckets, 0.2 ns up to 1024.
+  // (This is what made c = 19 a poor choice for the 255- / 253-bit curves at 2^24: 13 windows of 20 bits end on a full-width
+  // last window and win -- bls12-381 G1 105.0 -> 96.8 ms, bls12-377 G1 117.2 -> 114.2 ms, bn254 G1 at 2^25 86.8 -> 83.4 ms.)
+  if (p.nwin > 1 && p.nb_last <= 1024) tail += 1e-6 * (double)n * (p.nb_last <= 4 ? 0.35 : 0.2);
   const double e_ns = m.add_ns * (1.0 + 0.012 * std::max(0, c - 17)) + 0.009;
   return (double)n * p.nwin * e_ns * 1e-6 + tail;
 }

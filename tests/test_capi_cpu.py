@@ -101,7 +101,7 @@ def test_window_model_choices_are_pinned():
     L = native.lib()
     BN_G1, BN_G2, BLS_G1, BLS_G2, B377_G1 = 0, 1, 2, 3, 4
     want = {(BN_G1, 16): 15, (BN_G1, 18): 15, (BN_G1, 20): 17, (BN_G1, 22): 17, (BN_G1, 23): 17, (BN_G1, 24): 17, (BN_G1, 26): 20,
-            (BLS_G1, 20): 16, (BLS_G1, 22): 17, (BLS_G1, 24): 19, (BN_G2, 20): 17, (BN_G2, 22): 17, (BLS_G2, 20): 17, (B377_G1, 22): 17}
+            (BLS_G1, 20): 16, (BLS_G1, 22): 17, (BLS_G1, 23): 17, (BLS_G1, 24): 20, (BN_G1, 25): 20, (BN_G2, 24): 20, (B377_G1, 24): 20, (BN_G2, 20): 17, (BN_G2, 22): 17, (BLS_G2, 20): 17, (B377_G1, 22): 17}
     # N4 curves (profiles/r02_n4_new_curves_call11.txt, _call12.txt): secp256k1's 256-bit scalars make 16 | 256 and 20 (13 windows,
     # a full-width last one) the good widths -- 15, 17, 18, 19 leave a last window of 1..9 bits whose few buckets serialise K1
     SECP, BW6_G1, BW6_G2 = 6, 7, 8
@@ -110,6 +110,8 @@ def test_window_model_choices_are_pinned():
     # bls24-315 / bls24-317 G1, bw6-633 (profiles/r02_n4_more_curves_call13.txt, r02_n4_model_checks_call14.txt)
     B315, B317, BW633_G1, BW633_G2 = 9, 10, 11, 12
     want.update({(B315, 20): 17, (B315, 24): 20, (B317, 22): 17, (BW633_G1, 18): 15, (BW633_G1, 22): 18, (BW633_G2, 20): 16})
+    # (c = 20 entries: profiles/r02_c20_checks_call15.txt -- 13 windows of 20 bits end on a full-width last window; bls12-381 G1's
+    # earlier optimum c = 19 has a 9-bit last window whose 256 buckets serialise K1: 105.0 ms against 96.8)
     for (curve, logn), c in want.items():
         assert L.gmsm_choose_window_bits(curve, 1 << logn) == c, (curve, logn)
     for curve in (BN_G1, BN_G2, BLS_G1, BLS_G2, BW6_G1):
