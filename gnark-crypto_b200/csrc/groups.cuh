@@ -1,4 +1,4 @@
-// The four (curve, group) instantiations on the MultiExp path and their memory sizes.
+// The (curve, group) instantiations on the MultiExp path and their memory sizes: the four of the hot path, then next-row N4.
 //   bn254 G1 / G2       ecc/bn254/g1.go:18-30, g2.go:19-31, fr = ecc/bn254/fr (254 bits)
 //   bls12-381 G1 / G2   ecc/bls12-381/g1.go, g2.go, fr = ecc/bls12-381/fr (255 bits)
 #pragma once
