@@ -32,10 +32,11 @@ struct Error : std::runtime_error {  // the Go `error`
 template <int L>
 using Element = std::array<uint64_t, L>;
 
-template <gmsm_curve_t CURVE, int L, int EXT>  // EXT = 1: coordinates in Fp, 2: in Fp2 (E2{A0,A1})
+// EXT = 1: coordinates in Fp, 2: in Fp2 (E2{A0,A1}); LR = fr.Limbs (4; 5 for bw6-633, 6 for bw6-761)
+template <gmsm_curve_t CURVE, int L, int EXT, int LR = 4>
 struct Group {
   using Coord = std::array<uint64_t, L * EXT>;
-  using Scalar = Element<4>;  // fr.Element
+  using Scalar = Element<LR>;  // fr.Element
 
   struct Affine {  // G1Affine / G2Affine: {X, Y}; infinity = all zero (g1.go:41-47)
     Coord X{}, Y{};
@@ -139,5 +140,36 @@ using G1Jac = G1::Jac;
 using G2Affine = G2::Affine;
 using G2Jac = G2::Jac;
 }  // namespace bls12377
+namespace secp256k1 {   // ecc/secp256k1 (G1 only)
+using G1 = Group<GMSM_SECP256K1_G1, 4, 1>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+}  // namespace secp256k1
+namespace bw6761 {   // ecc/bw6-761: both groups over the 12-word Fp, fr.Element = [6]uint64
+using G1 = Group<GMSM_BW6761_G1, 12, 1, 6>;
+using G2 = Group<GMSM_BW6761_G2, 12, 1, 6>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+using G2Affine = G2::Affine;
+using G2Jac = G2::Jac;
+}  // namespace bw6761
+namespace bls24315 {   // ecc/bls24-315 (G1; G2 is over Fp4 and stays on the CPU path)
+using G1 = Group<GMSM_BLS24315_G1, 5, 1>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+}  // namespace bls24315
+namespace bls24317 {   // ecc/bls24-317 (G1)
+using G1 = Group<GMSM_BLS24317_G1, 5, 1>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+}  // namespace bls24317
+namespace bw6633 {   // ecc/bw6-633: both groups over the 10-word Fp, fr.Element = [5]uint64
+using G1 = Group<GMSM_BW6633_G1, 10, 1, 5>;
+using G2 = Group<GMSM_BW6633_G2, 10, 1, 5>;
+using G1Affine = G1::Affine;
+using G1Jac = G1::Jac;
+using G2Affine = G2::Affine;
+using G2Jac = G2::Jac;
+}  // namespace bw6633
 
 }  // namespace gmsm_host
