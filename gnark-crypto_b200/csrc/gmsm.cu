@@ -121,7 +121,7 @@ static const WidthModel& width_model(int curve) {
   static const WidthModel bw6761 = {1.63, {16.8, 16.5, 17.7, 19.3, 25.9, 30.2, 46.6}, 13.2, 33.4};
   // 10- and 20-limb groups (bls24-315 / bls24-317 G1, bw6-633): fitted from profiles/r02_n4_more_curves_call13.txt; bw6-633's
   // c = 17 entry absorbs an accumulate that is 6 % slower per addition at that width than at 16 or 18
-  static const WidthModel bls24_g1 = {0.272, {3.38, 3.30, 3.31, 3.50, 3.61, 4.95, 6.18}, 2.5, 3.62};
+  static const WidthModel bls24_g1 = {0.255, {3.38, 3.30, 3.31, 3.50, 3.61, 4.95, 6.18}, 2.5, 3.62};
   static const WidthModel bw6633 = {1.08, {13.05, 13.3, 12.4, 13.4, 19.6, 18.9, 28.2}, 9.5, 18.7};
   switch (curve) {
     case GMSM_SECP256K1_G1: return secp256k1_g1;
