@@ -352,7 +352,10 @@ def test_emulated_sharded_window_sums_and_finalize(g, tables):
         _check(g, out, want)
 
 
-@pytest.mark.parametrize("g,n", [("bn254_g1", 700), ("bls12381_g1", 260), ("bls12377_g1", 150), ("bn254_g2", 180), ("bls12381_g2", 100), ("bls12377_g2", 80)])
+@pytest.mark.parametrize("g,n", [("bn254_g1", 700), ("bls12381_g1", 260), ("bls12377_g1", 150), ("bn254_g2", 180), ("bls12381_g2", 100), ("bls12377_g2", 80),
+                                 # the groups whose contexts take the lane-parallel tail BY DEFAULT (gmsm.cu: bw6-761, bw6-633), and
+                                 # the full-width-modulus field through the same lane-parallel formulas
+                                 ("bw6761_g1", 70), ("bw6633_g2", 80), ("secp256k1_g1", 200)])
 def test_emulated_quad_tail(g, n):
     """the lane-parallel (quad) form of the tail kernels (csrc/quad.cuh: one point operation per four lanes, products of a
     formula step spread over the lanes and broadcast with masked shuffles) -- carry levels, segment reduction with its
